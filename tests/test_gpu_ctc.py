@@ -1,0 +1,125 @@
+"""GPU parity: csrc/ctc.cu through the C ABI vs the CTC oracle (oracle/ctc_ref.c, float64).
+Tolerance (north_star): relative 1e-5 in fp32 -> |cost - ref| <= 1e-5*max(1,|ref|) per utterance and
+max|grad - ref| <= 1e-5 (gradients are O(1): softmax minus occupancy)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.ctc_ref import ctc_ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _case(rng, T, B, A, Lmax, repeats=0.1, feasible=True):
+    acts = (rng.normal(size=(T, B, A)) * 1.5).astype(np.float32)
+    act_lens = np.sort(rng.integers(max(1, T // 2), T + 1, size=B))[::-1].astype(np.int32)
+    act_lens[0] = T
+    label_lens = np.zeros(B, np.int32)
+    labels = []
+    for b in range(B):
+        hi = min(Lmax, act_lens[b] // 2 if feasible else Lmax)
+        L = int(rng.integers(0, hi + 1))
+        lab = rng.integers(1, A, size=L)
+        for j in range(1, L):
+            if rng.random() < repeats:
+                lab[j] = lab[j - 1]
+        label_lens[b] = L
+        labels.extend(lab.tolist())
+    return acts, np.array(labels, np.int32), act_lens, label_lens
+
+
+def _run(cuda, acts, labels, act_lens, label_lens):
+    from vistaocr_b200.warpctc import ctc_costs_and_grads
+    costs, grads = ctc_costs_and_grads(torch.from_numpy(acts).to(cuda), torch.from_numpy(labels),
+                                       torch.from_numpy(act_lens), torch.from_numpy(label_lens))
+    return costs.cpu().numpy().astype(np.float64), grads.cpu().numpy()
+
+
+def _check(got_c, got_g, acts, labels, act_lens, label_lens):
+    want_c, want_g = ctc_ref(acts, labels, act_lens, label_lens)
+    np.testing.assert_allclose(got_c, want_c, rtol=RTOL, atol=RTOL)
+    assert np.abs(got_g - want_g).max() <= RTOL
+    T = acts.shape[0]
+    for b in range(acts.shape[1]):
+        assert not got_g[min(T, act_lens[b]):, b].any()  # exact zeros beyond act_len
+
+
+def test_known_answer(cuda):
+    acts = np.array([[[0.1, 0.6, 0.1, 0.1, 0.1]], [[0.1, 0.1, 0.6, 0.1, 0.1]]], np.float32)
+    c, g = _run(cuda, acts, np.array([1, 2], np.int32), np.array([2], np.int32), np.array([2], np.int32))
+    assert abs(c[0] - 2.4628584384918) < 1e-5
+    np.testing.assert_allclose(g[0, 0], [0.177031, -0.708125, 0.177031, 0.177031, 0.177031], atol=1e-5)
+
+
+@pytest.mark.parametrize("T,B,A,Lmax", [(50, 7, 11, 12), (100, 32, 80, 20), (37, 5, 121, 18), (200, 16, 97, 60),
+                                        (64, 9, 200, 31), (20, 3, 3, 10), (300, 4, 120, 150), (5, 70, 33, 2),
+                                        (12, 2, 3000, 5), (700, 2, 40, 300)])
+def test_ctc_matches_oracle(cuda, T, B, A, Lmax):
+    rng = np.random.default_rng(T + 31 * B + A)
+    case = _case(rng, T, B, A, Lmax)
+    c, g = _run(cuda, *case)
+    _check(c, g, *case)
+
+
+def test_infeasible_empty_and_single_frame(cuda):
+    rng = np.random.default_rng(11)
+    T, B, A = 9, 5, 6
+    acts = rng.normal(size=(T, B, A)).astype(np.float32)
+    # b0: infeasible (needs 2L-ish frames), b1: empty label, b2: single frame single label, b3: repeats need blanks
+    label_lens = np.array([8, 0, 1, 4, 3], np.int32)
+    act_lens = np.array([9, 7, 1, 7, 0], np.int32)
+    labels = np.array([1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 3, 3, 3, 1, 2, 3], np.int32)
+    c, g = _run(cuda, acts, labels, act_lens, label_lens)
+    _check(c, g, acts, labels, act_lens, label_lens)
+    assert c[0] == 0.0 and not g[:, 0].any()
+    assert c[4] == 0.0 and not g[:, 4].any()
+
+
+def test_module_autograd_and_host_cost(cuda):
+    from vistaocr_b200 import CTCLoss
+    rng = np.random.default_rng(2)
+    acts, labels, act_lens, label_lens = _case(rng, 40, 6, 30, 10)
+    x = torch.from_numpy(acts).to(cuda).requires_grad_(True)
+    crit = CTCLoss().cuda()
+    loss = crit(x, torch.from_numpy(labels), torch.from_numpy(act_lens), torch.from_numpy(label_lens))
+    assert loss.shape == (1,) and not loss.is_cuda  # warp-ctc returns a CPU FloatTensor[1]
+    loss.backward()
+    want_c, want_g = ctc_ref(acts, labels, act_lens, label_lens)
+    assert abs(loss.data[0].item() - want_c.sum()) <= RTOL * want_c.sum()
+    assert (x.grad.cpu().numpy() - want_g).__abs__().max() <= RTOL
+    # upstream chain rule: scaled loss scales the gradient
+    x2 = torch.from_numpy(acts).to(cuda).requires_grad_(True)
+    l2 = CTCLoss(host_cost=False)(x2, torch.from_numpy(labels), torch.from_numpy(act_lens),
+                                  torch.from_numpy(label_lens))
+    assert l2.is_cuda
+    (l2 * 0.5).sum().backward()
+    assert (x2.grad.cpu().numpy() - 0.5 * want_g).__abs__().max() <= RTOL
+
+
+def test_full_size_properties(cuda):
+    """cfg4 corner (T=1000, A=200, L<=150, B=256): checked through size-independent properties -
+    grad rows sum to 0, grads vanish beyond act_len, cost is invariant to a per-frame shift of the activations,
+    and a float64 oracle spot check on 3 utterances."""
+    from vistaocr_b200.warpctc import ctc_costs_and_grads
+    rng = np.random.default_rng(4)
+    T, B, A, Lmax = 1000, 256, 200, 150
+    acts, labels, act_lens, label_lens = _case(rng, T, B, A, Lmax)
+    xa = torch.from_numpy(acts).to(cuda)
+    args = (torch.from_numpy(labels), torch.from_numpy(act_lens), torch.from_numpy(label_lens))
+    costs, grads = ctc_costs_and_grads(xa, *args)
+    assert torch.isfinite(costs).all() and (costs >= 0).all()
+    assert grads.sum(2).abs().max().item() < 1e-4
+    tt = torch.arange(T, device=cuda)[:, None]
+    beyond = tt >= torch.from_numpy(act_lens).to(cuda)[None, :]
+    assert grads[beyond].abs().max().item() == 0.0
+    shift = torch.randn((T, B, 1), device=cuda)
+    costs2, _ = ctc_costs_and_grads((xa + shift).contiguous(), *args, want_grads=False)
+    assert ((costs2 - costs).abs() <= 2e-5 * costs.abs().clamp(min=1)).all()
+    offs = np.concatenate([[0], np.cumsum(label_lens)])
+    for b in (0, 100, 255):
+        sub = (acts[:, b:b + 1].copy(), labels[offs[b]:offs[b + 1]], act_lens[b:b + 1], label_lens[b:b + 1])
+        wc, wg = ctc_ref(*sub)
+        assert abs(costs[b].item() - wc[0]) <= RTOL * max(1.0, wc[0])
+        assert np.abs(grads[:, b].cpu().numpy() - wg[:, 0]).max() <= RTOL

@@ -1,0 +1,383 @@
+// CTC loss forward + gradient on sm_100a, log-space fp32, blank = 0, softmax inside.
+// Replaces warpctc_pytorch.CTCLoss / warp-ctc's compute_ctc_loss (reference call sites
+// src/train_cnn_lstm.py:12,52,138,358).  Four launches per batch:
+//   1. ctc_prep_kernel        label offsets (exclusive scan) + per-position "next same symbol" chains
+//   2. ctc_lse_lattice_kernel streaming pass #1 over acts: row log-sum-exp (warp-shuffle max/sum) and the compact
+//                             log-softmax lattice  lat[b][t][0]=blank, lat[b][t][1+j]=label j   (L+1 floats/frame)
+//   3. ctc_alpha_beta_kernel  one CTA per utterance; an alpha warp-group walks t forward while a beta warp-group
+//                             walks t backward CONCURRENTLY over the blank-extended lattice (S=2L+1 states),
+//                             one __syncthreads per time step for both; alpha/beta lattices go to the workspace
+//   4. ctc_grad_kernel        streaming pass #2 over acts: softmax - occupancy, written once; rows beyond
+//                             act_len and infeasible utterances are written as exact zeros
+// Passes 2 and 4 stage flat row tiles of acts in shared memory with a 1-D bulk async copy (see decode.cu).
+// Algorithmic HBM bytes: 2*T*B*A*4 (acts read once if pass 4 hits L2, grads written once); the lattices add
+// 4*S/A of that.
+#include "common.cuh"
+
+namespace vocr {
+
+constexpr int kCtcThreads = 256;
+constexpr int kCtcWarps = kCtcThreads / 32;
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == kNegInf) return kNegInf;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == kNegInf) return kNegInf;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+
+struct CtcWorkspace {
+  int32_t* offsets;  // [B+1]
+  int32_t* nxt;      // [sum L] next position with the same symbol, -1 if none
+  int32_t* first;    // [sum L] 1 if no earlier position has the same symbol
+  float* ll;         // [B] log-likelihood (-inf = infeasible)
+  float* lse;        // [B*T]
+  float* lat;        // [B*T*(Lmax+1)]
+  float* alpha;      // [B*T*Smax]
+  float* beta;       // [B*T*Smax]
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+__host__ inline size_t ctc_carve(CtcWorkspace* ws, void* base, int T, int B, int max_label_len) {
+  const size_t Lmax = (size_t)max_label_len, Smax = 2 * Lmax + 1;
+  size_t off = 0;
+  unsigned char* p = static_cast<unsigned char*>(base);
+  auto take = [&](size_t bytes) {
+    unsigned char* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  int32_t* offsets = (int32_t*)take(sizeof(int32_t) * ((size_t)B + 1));
+  int32_t* nxt = (int32_t*)take(sizeof(int32_t) * (size_t)B * Lmax + 4);
+  int32_t* first = (int32_t*)take(sizeof(int32_t) * (size_t)B * Lmax + 4);
+  float* ll = (float*)take(sizeof(float) * (size_t)B);
+  float* lse = (float*)take(sizeof(float) * (size_t)B * T);
+  float* lat = (float*)take(sizeof(float) * (size_t)B * T * (Lmax + 1));
+  float* alpha = (float*)take(sizeof(float) * (size_t)B * T * Smax);
+  float* beta = (float*)take(sizeof(float) * (size_t)B * T * Smax);
+  if (ws) *ws = CtcWorkspace{offsets, nxt, first, ll, lse, lat, alpha, beta};
+  return off;
+}
+
+// ---- 1. prep -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ctc_prep_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens, int B, int Lmax,
+                CtcWorkspace ws) {
+  __shared__ int s_part[1024];
+  // exclusive scan of label_lens (B is small: one CTA, chunked serial-by-thread scan)
+  const int per = ceil_div(B, (int)blockDim.x);
+  const int lo = min(B, (int)threadIdx.x * per), hi = min(B, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += max(0, min(label_lens[i], Lmax));
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) {
+      const int v = s_part[i];
+      s_part[i] = run;
+      run += v;
+    }
+    ws.offsets[B] = run;
+  }
+  __syncthreads();
+  int run = s_part[threadIdx.x];
+  for (int i = lo; i < hi; ++i) {
+    ws.offsets[i] = run;
+    run += max(0, min(label_lens[i], Lmax));
+  }
+  __syncthreads();
+  // duplicate chains: thread per utterance-position pair (strided)
+  for (int b = 0; b < B; ++b) {
+    const int L = max(0, min(label_lens[b], Lmax));
+    const int off = ws.offsets[b];
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+      const int sym = labels[off + j];
+      int nx = -1, fi = 1;
+      for (int q = j + 1; q < L; ++q)
+        if (labels[off + q] == sym) {
+          nx = q;
+          break;
+        }
+      for (int q = 0; q < j; ++q)
+        if (labels[off + q] == sym) {
+          fi = 0;
+          break;
+        }
+      ws.nxt[off + j] = nx;
+      ws.first[off + j] = fi;
+    }
+  }
+}
+
+// ---- 2. row LSE + compact lattice --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtcThreads)
+ctc_lse_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, int B, int A, int rows_per_tile,
+                       bool base_aligned, const int32_t* __restrict__ labels,
+                       const int32_t* __restrict__ label_lens, const int32_t* __restrict__ act_lens, int Lmax,
+                       CtcWorkspace ws) {
+  extern __shared__ __align__(128) unsigned char ctc_smem[];
+  const long long row0 = (long long)blockIdx.x * rows_per_tile;
+  const int rows_here = (int)min((long long)rows_per_tile, n_rows - row0);
+  // skip tiles that lie entirely beyond every utterance's length (rows are time-major: tile covers few t)
+  const float* tile = stage_row_tile(ctc_smem, acts + row0 * A, rows_here * A, base_aligned);
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  for (int r = warp; r < rows_here; r += kCtcWarps) {
+    const long long gr = row0 + r;
+    const int t = (int)(gr / B), b = (int)(gr % B);
+    if (t >= act_lens[b]) continue;
+    const float* row = tile + (size_t)r * A;
+    float m = kNegInf;
+    for (int a = lane; a < A; a += 32) m = fmaxf(m, row[a]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int a = lane; a < A; a += 32) s += expf(row[a] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    const size_t bt = (size_t)b * T + t;
+    if (lane == 0) ws.lse[bt] = lse;
+    const int L = max(0, min(label_lens[b], Lmax));
+    const int off = ws.offsets[b];
+    float* lat = ws.lat + bt * (size_t)(Lmax + 1);
+    for (int j = lane; j <= L; j += 32) {
+      int sym = (j == 0) ? 0 : labels[off + j - 1];
+      sym = max(0, min(sym, A - 1));
+      lat[j] = row[sym] - lse;
+    }
+  }
+}
+
+// ---- 3. alpha / beta recursions ----------------------------------------------------------------------------
+// block = 2*G threads: threads [0,G) own alpha, [G,2G) own beta.  dynamic smem: int lab[Smax] + float buf[2][2][Smax]
+__global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens,
+                                      const int32_t* __restrict__ act_lens, int T, int B, int A, int Lmax, int G,
+                                      CtcWorkspace ws, float* __restrict__ costs) {
+  extern __shared__ __align__(16) unsigned char ab_smem[];
+  const int Smax = 2 * Lmax + 1;
+  int* lab = reinterpret_cast<int*>(ab_smem);
+  float* bufs = reinterpret_cast<float*>(ab_smem + sizeof(int) * (size_t)Smax);
+  const int b = blockIdx.x;
+  const int L = max(0, min(label_lens[b], Lmax));
+  const int S = 2 * L + 1;
+  const int Tb = max(0, min(act_lens[b], T));
+  const int grp = threadIdx.x / G;  // 0 alpha, 1 beta
+  const int tid = threadIdx.x - grp * G;
+  const int off = ws.offsets[b];
+  if (Tb == 0) {
+    if (threadIdx.x == 0) {
+      // zero frames: p(empty labelling) = 1, anything else is infeasible -> cost 0 either way, grads are moot
+      ws.ll[b] = (L == 0) ? 0.f : kNegInf;
+      costs[b] = 0.f;
+    }
+    return;
+  }
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    int sym = 0;
+    if (s & 1) sym = max(0, min(labels[off + (s >> 1)], A - 1));
+    lab[s] = sym;
+  }
+  __syncthreads();
+  float* my = bufs + (size_t)grp * 2 * Smax;  // [2][Smax] ping-pong
+  float* out_lat = (grp == 0 ? ws.alpha : ws.beta) + (size_t)b * T * Smax;
+  const float* lat = ws.lat + (size_t)b * T * (Lmax + 1);
+  const int Lp1 = Lmax + 1;
+
+  // step 0
+  {
+    const int t = (grp == 0) ? 0 : Tb - 1;
+    for (int s = tid; s < S; s += G) {
+      const float lp = lat[(size_t)t * Lp1 + ((s & 1) ? (s >> 1) + 1 : 0)];
+      float v = kNegInf;
+      if (grp == 0) {
+        if (s <= 1) v = lp;
+      } else {
+        if (s >= S - 2) v = lp;
+      }
+      my[s] = v;
+      out_lat[(size_t)t * Smax + s] = v;
+    }
+  }
+  __syncthreads();
+  for (int k = 1; k < Tb; ++k) {
+    const int t = (grp == 0) ? k : Tb - 1 - k;
+    const float* prev = my + (size_t)((k - 1) & 1) * Smax;
+    float* cur = my + (size_t)(k & 1) * Smax;
+    for (int s = tid; s < S; s += G) {
+      const float lp = lat[(size_t)t * Lp1 + ((s & 1) ? (s >> 1) + 1 : 0)];
+      float a0 = prev[s], a1 = kNegInf, a2 = kNegInf;
+      if (grp == 0) {
+        if (s >= 1) a1 = prev[s - 1];
+        if ((s & 1) && s >= 3 && lab[s] != lab[s - 2]) a2 = prev[s - 2];
+      } else {
+        if (s + 1 < S) a1 = prev[s + 1];
+        if ((s & 1) && s + 2 < S && lab[s] != lab[s + 2]) a2 = prev[s + 2];
+      }
+      const float v = lse3(a0, a1, a2) + lp;
+      cur[s] = v;
+      out_lat[(size_t)t * Smax + s] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float* fin = bufs + (size_t)((Tb - 1) & 1) * Smax;  // alpha at t = Tb-1
+    const float ll = lse2(fin[S - 1], (S >= 2) ? fin[S - 2] : kNegInf);
+    ws.ll[b] = ll;
+    costs[b] = (ll == kNegInf) ? 0.f : -ll;
+  }
+}
+
+// ---- 4. gradient ------------------------------------------------------------------------------------------
+// dynamic smem: 16 B mbarrier + tile + per-warp occupancy scratch kCtcWarps*Smax floats
+__global__ void __launch_bounds__(kCtcThreads)
+ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, long long n_rows, int T, int B, int A,
+                int rows_per_tile, bool base_aligned, const int32_t* __restrict__ labels,
+                const int32_t* __restrict__ label_lens, const int32_t* __restrict__ act_lens, int Lmax,
+                CtcWorkspace ws) {
+  extern __shared__ __align__(128) unsigned char ctc_smem[];
+  const int Smax = 2 * Lmax + 1;
+  // walk tiles from the end: the rows touched last by pass 2 are the most likely to still sit in L2
+  const long long tile_idx = (long long)gridDim.x - 1 - blockIdx.x;
+  const long long row0 = tile_idx * rows_per_tile;
+  const int rows_here = (int)min((long long)rows_per_tile, n_rows - row0);
+  float* tile = stage_row_tile(ctc_smem, acts + row0 * A, rows_here * A, base_aligned);
+  const size_t tile_floats = (size_t)rows_per_tile * A;
+  float* scratch = tile + ((tile_floats + 3) & ~size_t(3));
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* gs = scratch + (size_t)warp * Smax;
+  for (int r = warp; r < rows_here; r += kCtcWarps) {
+    const long long gr = row0 + r;
+    const int t = (int)(gr / B), b = (int)(gr % B);
+    float* row = tile + (size_t)r * A;
+    const float ll = ws.ll[b];
+    if (t >= act_lens[b] || ll == kNegInf) {
+      for (int a = lane; a < A; a += 32) row[a] = 0.f;
+      continue;
+    }
+    const size_t bt = (size_t)b * T + t;
+    const float lse = ws.lse[bt];
+    for (int a = lane; a < A; a += 32) row[a] = expf(row[a] - lse);
+    const int L = max(0, min(label_lens[b], Lmax));
+    const int S = 2 * L + 1;
+    const int off = ws.offsets[b];
+    const float* al = ws.alpha + bt * (size_t)Smax;
+    const float* be = ws.beta + bt * (size_t)Smax;
+    const float* lat = ws.lat + bt * (size_t)(Lmax + 1);
+    float blank_occ = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      const float lp = lat[(s & 1) ? (s >> 1) + 1 : 0];
+      const float ab = al[s] + be[s];
+      // beta carries the emission at t as well as alpha: remove one copy; -inf states contribute 0
+      const float g = (ab == kNegInf) ? 0.f : expf(ab - lp - ll);
+      if (s & 1) gs[s >> 1] = g;
+      else blank_occ += g;
+    }
+    blank_occ = warp_sum(blank_occ);
+    __syncwarp();
+    if (lane == 0) row[0] -= blank_occ;
+    for (int j = lane; j < L; j += 32) {
+      if (ws.first[off + j]) {
+        float tot = 0.f;
+        for (int q = j; q >= 0; q = ws.nxt[off + q]) tot += gs[q];
+        const int sym = max(0, min(labels[off + j], A - 1));
+        row[sym] -= tot;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // write the whole tile back, coalesced
+  float* gdst = grads + row0 * A;
+  const int n = rows_here * A;
+  if (base_aligned && (n % 4) == 0) {
+    const float4* src4 = reinterpret_cast<const float4*>(tile);
+    float4* dst4 = reinterpret_cast<float4*>(gdst);
+    for (int i = threadIdx.x; i < n / 4; i += kCtcThreads) dst4[i] = src4[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += kCtcThreads) gdst[i] = tile[i];
+  }
+}
+
+}  // namespace vocr
+
+using namespace vocr;
+
+extern "C" size_t vocr_ctc_workspace_size(int T, int B, int A, int max_label_len) {
+  (void)A;
+  if (T < 0 || B < 0 || max_label_len < 0) return 0;
+  return ctc_carve(nullptr, nullptr, T, B, max_label_len) + 256;
+}
+
+extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t* labels, const int32_t* label_lens,
+                                 const int32_t* act_lens, int T, int B, int A, int max_label_len, float* costs,
+                                 void* workspace, size_t workspace_bytes, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(T >= 0 && B >= 0 && A >= 1 && max_label_len >= 0);
+  if (B == 0) return VOCR_OK;
+  VOCR_REQUIRE(label_lens && act_lens && costs && workspace);
+  VOCR_REQUIRE(labels || max_label_len == 0);
+  VOCR_REQUIRE(T == 0 || acts);
+  uintptr_t wbase = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  CtcWorkspace ws;
+  const size_t need = ctc_carve(&ws, reinterpret_cast<void*>(wbase), T, B, max_label_len);
+  VOCR_REQUIRE(need + (wbase - reinterpret_cast<uintptr_t>(workspace)) <= workspace_bytes);
+  const int Lmax = max_label_len, Smax = 2 * Lmax + 1;
+  static const int32_t kDummy = 0;
+  const int32_t* labels_safe = labels ? labels : &kDummy;  // never dereferenced when Lmax == 0
+
+  ctc_prep_kernel<<<1, 1024, 0, stream>>>(labels_safe, label_lens, B, Lmax, ws);
+  VOCR_CHECK_LAUNCH();
+
+  const long long n_rows = (long long)T * B;
+  int rows_per_tile = 32;
+  while (rows_per_tile > 4 && (size_t)rows_per_tile * A * 4 > 32768) rows_per_tile >>= 1;
+  const size_t tile_bytes = ((size_t)rows_per_tile * A * 4 + 15) & ~size_t(15);
+  const bool base_aligned = (reinterpret_cast<uintptr_t>(acts) % 16 == 0) &&
+                            (grads == nullptr || reinterpret_cast<uintptr_t>(grads) % 16 == 0);
+  const long long n_tiles = ceil_div64(n_rows, rows_per_tile);
+  VOCR_REQUIRE(n_tiles < (1ll << 31));
+  if (n_rows > 0) {
+    const size_t smem2 = 16 + tile_bytes;
+    if (smem2 > 48 * 1024) {
+      VOCR_REQUIRE(smem2 <= 200 * 1024);
+      if (cudaFuncSetAttribute(ctc_lse_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) !=
+          cudaSuccess)
+        return VOCR_EXECUTION_FAILED;
+    }
+    ctc_lse_lattice_kernel<<<(unsigned)n_tiles, kCtcThreads, smem2, stream>>>(
+        acts, n_rows, T, B, A, rows_per_tile, base_aligned, labels_safe, label_lens, act_lens, Lmax, ws);
+    VOCR_CHECK_LAUNCH();
+  }
+  {
+    int G = ((Smax + 31) / 32) * 32;
+    if (G > 512) G = 512;
+    const size_t smem3 = sizeof(int) * (size_t)Smax + sizeof(float) * 4 * (size_t)Smax;
+    if (smem3 > 48 * 1024) {
+      VOCR_REQUIRE(smem3 <= 200 * 1024);
+      if (cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3) !=
+          cudaSuccess)
+        return VOCR_EXECUTION_FAILED;
+    }
+    ctc_alpha_beta_kernel<<<B, 2 * G, smem3, stream>>>(labels_safe, label_lens, act_lens, T, B, A, Lmax, G, ws,
+                                                       costs);
+    VOCR_CHECK_LAUNCH();
+  }
+  if (grads && n_rows > 0) {
+    const size_t smem4 = 16 + tile_bytes + sizeof(float) * (size_t)kCtcWarps * Smax + 16;
+    if (smem4 > 48 * 1024) {
+      VOCR_REQUIRE(smem4 <= 200 * 1024);
+      if (cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) !=
+          cudaSuccess)
+        return VOCR_EXECUTION_FAILED;
+    }
+    ctc_grad_kernel<<<(unsigned)n_tiles, kCtcThreads, smem4, stream>>>(acts, grads, n_rows, T, B, A, rows_per_tile,
+                                                                       base_aligned, labels_safe, label_lens,
+                                                                       act_lens, Lmax, ws);
+    VOCR_CHECK_LAUNCH();
+  }
+  return VOCR_OK;
+}
