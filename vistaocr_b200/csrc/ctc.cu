@@ -1,12 +1,14 @@
 // CTC loss forward + gradient on sm_100a, log-space fp32, blank = 0, softmax inside.
 // Replaces warpctc_pytorch.CTCLoss / warp-ctc's compute_ctc_loss (reference call sites
 // src/train_cnn_lstm.py:12,52,138,358).  Four launches per batch:
-//   1. ctc_prep_kernel        label offsets (exclusive scan) + per-position "next same symbol" chains
+//   1. ctc_scan_kernel        label offsets (exclusive scan of label_lens)
 //   2. ctc_lse_lattice_kernel streaming pass #1 over acts: row log-sum-exp (warp-shuffle max/sum) and the compact
 //                             log-softmax lattice  lat[b][t][0]=blank, lat[b][t][1+j]=label j   (L+1 floats/frame)
 //   3. ctc_alpha_beta_kernel  one CTA per utterance; an alpha warp-group walks t forward while a beta warp-group
 //                             walks t backward CONCURRENTLY over the blank-extended lattice (S=2L+1 states),
-//                             one __syncthreads per time step for both; alpha/beta lattices go to the workspace
+//                             one __syncthreads per time step for both; the lattice is streamed through shared
+//                             memory by bulk async copies; alpha/beta are renormalised every 8 steps (float64
+//                             offsets) so fp32 error does not grow with |log p|; lattices go to the workspace
 //   4. ctc_grad_kernel        streaming pass #2 over acts: softmax - occupancy, written once; rows beyond
 //                             act_len and infeasible utterances are written as exact zeros
 // Passes 2 and 4 stage flat row tiles of acts in shared memory with a 1-D bulk async copy (see decode.cu).
@@ -30,21 +32,27 @@ __device__ __forceinline__ float lse2(float a, float b) {
   return m + logf(expf(a - m) + expf(b - m));
 }
 
+constexpr int kCtcChunk = 16;  // lattice frames staged per bulk copy in the recursion kernel
+constexpr int kCtcRenorm = 8;  // renormalise alpha/beta every this many steps
+
 struct CtcWorkspace {
   int32_t* offsets;  // [B+1]
   int32_t* nxt;      // [sum L] next position with the same symbol, -1 if none
   int32_t* first;    // [sum L] 1 if no earlier position has the same symbol
-  float* ll;         // [B] log-likelihood (-inf = infeasible)
+  double* ll;        // [B] log-likelihood (-inf = infeasible)
+  double* offa;      // [B*T] cumulative renormalisation offset of alpha at frame t
+  double* offb;      // [B*T] same for beta
   float* lse;        // [B*T]
-  float* lat;        // [B*T*(Lmax+1)]
-  float* alpha;      // [B*T*Smax]
-  float* beta;       // [B*T*Smax]
+  float* lat;        // [B*T*Lp] compact log-softmax lattice, Lp = round_up(Lmax+1, 4)
+  float* alpha;      // [B*T*Smax] renormalised alpha
+  float* beta;       // [B*T*Smax] renormalised beta
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+__host__ __device__ inline int lat_stride(int Lmax) { return (Lmax + 1 + 3) & ~3; }
 
 __host__ inline size_t ctc_carve(CtcWorkspace* ws, void* base, int T, int B, int max_label_len) {
-  const size_t Lmax = (size_t)max_label_len, Smax = 2 * Lmax + 1;
+  const size_t Lmax = (size_t)max_label_len, Smax = 2 * Lmax + 1, Lp = (size_t)lat_stride(max_label_len);
   size_t off = 0;
   unsigned char* p = static_cast<unsigned char*>(base);
   auto take = [&](size_t bytes) {
@@ -52,67 +60,44 @@ __host__ inline size_t ctc_carve(CtcWorkspace* ws, void* base, int T, int B, int
     off += align256(bytes);
     return r;
   };
-  int32_t* offsets = (int32_t*)take(sizeof(int32_t) * ((size_t)B + 1));
-  int32_t* nxt = (int32_t*)take(sizeof(int32_t) * (size_t)B * Lmax + 4);
-  int32_t* first = (int32_t*)take(sizeof(int32_t) * (size_t)B * Lmax + 4);
-  float* ll = (float*)take(sizeof(float) * (size_t)B);
-  float* lse = (float*)take(sizeof(float) * (size_t)B * T);
-  float* lat = (float*)take(sizeof(float) * (size_t)B * T * (Lmax + 1));
-  float* alpha = (float*)take(sizeof(float) * (size_t)B * T * Smax);
-  float* beta = (float*)take(sizeof(float) * (size_t)B * T * Smax);
-  if (ws) *ws = CtcWorkspace{offsets, nxt, first, ll, lse, lat, alpha, beta};
+  CtcWorkspace w;
+  w.offsets = (int32_t*)take(sizeof(int32_t) * ((size_t)B + 1));
+  w.nxt = (int32_t*)take(sizeof(int32_t) * (size_t)B * Lmax + 4);
+  w.first = (int32_t*)take(sizeof(int32_t) * (size_t)B * Lmax + 4);
+  w.ll = (double*)take(sizeof(double) * (size_t)B);
+  w.offa = (double*)take(sizeof(double) * (size_t)B * T);
+  w.offb = (double*)take(sizeof(double) * (size_t)B * T);
+  w.lse = (float*)take(sizeof(float) * (size_t)B * T);
+  w.lat = (float*)take(sizeof(float) * (size_t)B * T * Lp);
+  w.alpha = (float*)take(sizeof(float) * (size_t)B * T * Smax);
+  w.beta = (float*)take(sizeof(float) * (size_t)B * T * Smax);
+  if (ws) *ws = w;
   return off;
 }
 
-// ---- 1. prep -----------------------------------------------------------------------------------------------
+// ---- 1. label offsets: exclusive scan of label_lens, one CTA, parallel --------------------------------------
 __global__ void __launch_bounds__(1024)
-ctc_prep_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens, int B, int Lmax,
-                CtcWorkspace ws) {
+ctc_scan_kernel(const int32_t* __restrict__ label_lens, int B, int Lmax, CtcWorkspace ws) {
   __shared__ int s_part[1024];
-  // exclusive scan of label_lens (B is small: one CTA, chunked serial-by-thread scan)
   const int per = ceil_div(B, (int)blockDim.x);
   const int lo = min(B, (int)threadIdx.x * per), hi = min(B, lo + per);
   int sum = 0;
   for (int i = lo; i < hi; ++i) sum += max(0, min(label_lens[i], Lmax));
   s_part[threadIdx.x] = sum;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < (int)blockDim.x; ++i) {
-      const int v = s_part[i];
-      s_part[i] = run;
-      run += v;
-    }
-    ws.offsets[B] = run;
+  // Hillis-Steele inclusive scan over the 1024 partials
+  for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+    const int v = (threadIdx.x >= (unsigned)d) ? s_part[threadIdx.x - d] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
   }
-  __syncthreads();
-  int run = s_part[threadIdx.x];
+  int run = s_part[threadIdx.x] - sum;  // exclusive
   for (int i = lo; i < hi; ++i) {
     ws.offsets[i] = run;
     run += max(0, min(label_lens[i], Lmax));
   }
-  __syncthreads();
-  // duplicate chains: thread per utterance-position pair (strided)
-  for (int b = 0; b < B; ++b) {
-    const int L = max(0, min(label_lens[b], Lmax));
-    const int off = ws.offsets[b];
-    for (int j = threadIdx.x; j < L; j += blockDim.x) {
-      const int sym = labels[off + j];
-      int nx = -1, fi = 1;
-      for (int q = j + 1; q < L; ++q)
-        if (labels[off + q] == sym) {
-          nx = q;
-          break;
-        }
-      for (int q = 0; q < j; ++q)
-        if (labels[off + q] == sym) {
-          fi = 0;
-          break;
-        }
-      ws.nxt[off + j] = nx;
-      ws.first[off + j] = fi;
-    }
-  }
+  if (threadIdx.x == blockDim.x - 1) ws.offsets[B] = s_part[threadIdx.x];
 }
 
 // ---- 2. row LSE + compact lattice --------------------------------------------------------------------------
@@ -124,9 +109,9 @@ ctc_lse_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, 
   extern __shared__ __align__(128) unsigned char ctc_smem[];
   const long long row0 = (long long)blockIdx.x * rows_per_tile;
   const int rows_here = (int)min((long long)rows_per_tile, n_rows - row0);
-  // skip tiles that lie entirely beyond every utterance's length (rows are time-major: tile covers few t)
   const float* tile = stage_row_tile(ctc_smem, acts + row0 * A, rows_here * A, base_aligned);
   const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int Lp = lat_stride(Lmax);
   for (int r = warp; r < rows_here; r += kCtcWarps) {
     const long long gr = row0 + r;
     const int t = (int)(gr / B), b = (int)(gr % B);
@@ -143,7 +128,7 @@ ctc_lse_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, 
     if (lane == 0) ws.lse[bt] = lse;
     const int L = max(0, min(label_lens[b], Lmax));
     const int off = ws.offsets[b];
-    float* lat = ws.lat + bt * (size_t)(Lmax + 1);
+    float* lat = ws.lat + bt * (size_t)Lp;
     for (int j = lane; j <= L; j += 32) {
       int sym = (j == 0) ? 0 : labels[off + j - 1];
       sym = max(0, min(sym, A - 1));
@@ -153,14 +138,23 @@ ctc_lse_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, 
 }
 
 // ---- 3. alpha / beta recursions ----------------------------------------------------------------------------
-// block = 2*G threads: threads [0,G) own alpha, [G,2G) own beta.  dynamic smem: int lab[Smax] + float buf[2][2][Smax]
+// block = 2*G threads: threads [0,G) own alpha (t ascending), [G,2G) own beta (t descending), in lock step with
+// one __syncthreads per time step.  The compact lattice is streamed through shared memory kCtcChunk frames at a
+// time with 1-D bulk async copies (double buffered per direction).  Every kCtcRenorm steps the state vector is
+// renormalised by its maximum and the subtracted amount accumulated in float64, so the stored alpha/beta stay
+// O(1)-O(10) in magnitude: fp32 log-space error no longer grows with |log p| (warp-ctc's does).
+// dynamic smem: [mbarriers 4x8][lab Smax][bufs 2x2xSmax][wmax 2x32][lattice 2x2xkCtcChunk*Lp]
 __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens,
                                       const int32_t* __restrict__ act_lens, int T, int B, int A, int Lmax, int G,
                                       CtcWorkspace ws, float* __restrict__ costs) {
-  extern __shared__ __align__(16) unsigned char ab_smem[];
+  extern __shared__ __align__(128) unsigned char ab_smem[];
   const int Smax = 2 * Lmax + 1;
-  int* lab = reinterpret_cast<int*>(ab_smem);
-  float* bufs = reinterpret_cast<float*>(ab_smem + sizeof(int) * (size_t)Smax);
+  const int Lp = lat_stride(Lmax);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ab_smem);                  // [2 grp][2 buf]
+  float* latbuf = reinterpret_cast<float*>(ab_smem + 32);                 // [2][2][kCtcChunk*Lp] (16-B aligned)
+  float* bufs = latbuf + (size_t)4 * kCtcChunk * Lp;                      // [2][2][Smax]
+  float* wmax = bufs + (size_t)4 * Smax;                                  // [2][32]
+  int* lab = reinterpret_cast<int*>(wmax + 64);                           // [Smax]
   const int b = blockIdx.x;
   const int L = max(0, min(label_lens[b], Lmax));
   const int S = 2 * L + 1;
@@ -168,66 +162,121 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
   const int grp = threadIdx.x / G;  // 0 alpha, 1 beta
   const int tid = threadIdx.x - grp * G;
   const int off = ws.offsets[b];
-  if (Tb == 0) {
-    if (threadIdx.x == 0) {
-      // zero frames: p(empty labelling) = 1, anything else is infeasible -> cost 0 either way, grads are moot
-      ws.ll[b] = (L == 0) ? 0.f : kNegInf;
-      costs[b] = 0.f;
-    }
-    return;
-  }
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     int sym = 0;
     if (s & 1) sym = max(0, min(labels[off + (s >> 1)], A - 1));
     lab[s] = sym;
   }
-  __syncthreads();
-  float* my = bufs + (size_t)grp * 2 * Smax;  // [2][Smax] ping-pong
-  float* out_lat = (grp == 0 ? ws.alpha : ws.beta) + (size_t)b * T * Smax;
-  const float* lat = ws.lat + (size_t)b * T * (Lmax + 1);
-  const int Lp1 = Lmax + 1;
-
-  // step 0
-  {
-    const int t = (grp == 0) ? 0 : Tb - 1;
-    for (int s = tid; s < S; s += G) {
-      const float lp = lat[(size_t)t * Lp1 + ((s & 1) ? (s >> 1) + 1 : 0)];
-      float v = kNegInf;
-      if (grp == 0) {
-        if (s <= 1) v = lp;
-      } else {
-        if (s >= S - 2) v = lp;
-      }
-      my[s] = v;
-      out_lat[(size_t)t * Smax + s] = v;
-    }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
   }
   __syncthreads();
-  for (int k = 1; k < Tb; ++k) {
-    const int t = (grp == 0) ? k : Tb - 1 - k;
-    const float* prev = my + (size_t)((k - 1) & 1) * Smax;
-    float* cur = my + (size_t)(k & 1) * Smax;
-    for (int s = tid; s < S; s += G) {
-      const float lp = lat[(size_t)t * Lp1 + ((s & 1) ? (s >> 1) + 1 : 0)];
-      float a0 = prev[s], a1 = kNegInf, a2 = kNegInf;
-      if (grp == 0) {
-        if (s >= 1) a1 = prev[s - 1];
-        if ((s & 1) && s >= 3 && lab[s] != lab[s - 2]) a2 = prev[s - 2];
-      } else {
-        if (s + 1 < S) a1 = prev[s + 1];
-        if ((s & 1) && s + 2 < S && lab[s] != lab[s + 2]) a2 = prev[s + 2];
+  // duplicate-symbol chains for the gradient kernel (label positions j = 0..L-1, symbol lab[2j+1])
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    const int sym = lab[2 * j + 1];
+    int nx = -1, fi = 1;
+    for (int q = j + 1; q < L; ++q)
+      if (lab[2 * q + 1] == sym) {
+        nx = q;
+        break;
       }
-      const float v = lse3(a0, a1, a2) + lp;
-      cur[s] = v;
-      out_lat[(size_t)t * Smax + s] = v;
+    for (int q = 0; q < j; ++q)
+      if (lab[2 * q + 1] == sym) {
+        fi = 0;
+        break;
+      }
+    ws.nxt[off + j] = nx;
+    ws.first[off + j] = fi;
+  }
+  if (Tb == 0) {
+    if (threadIdx.x == 0) {
+      ws.ll[b] = (L == 0) ? 0.0 : -INFINITY;  // zero frames: only the empty labelling is feasible; cost 0 either way
+      costs[b] = 0.f;
     }
-    __syncthreads();
+    return;
+  }
+  float* my = bufs + (size_t)grp * 2 * Smax;  // [2][Smax] ping-pong
+  float* mylat = latbuf + (size_t)grp * 2 * kCtcChunk * Lp;
+  float* out_lat = (grp == 0 ? ws.alpha : ws.beta) + (size_t)b * T * Smax;
+  double* out_off = (grp == 0 ? ws.offa : ws.offb) + (size_t)b * T;
+  const float* lat_g = ws.lat + (size_t)b * T * Lp;
+  const int nchunks = ceil_div(Tb, kCtcChunk);
+  const int nwarps_g = G >> 5;
+  double offset = 0.0;  // meaningful in tid == 0 of each group
+
+  auto issue = [&](int c) {  // called by tid == 0 of each group
+    const int k0 = c * kCtcChunk, k1 = min(Tb, k0 + kCtcChunk);
+    const int t_lo = (grp == 0) ? k0 : Tb - k1;  // beta frames Tb-1-k for k in [k0,k1)  ->  [Tb-k1, Tb-1-k0]
+    const uint32_t bytes = (uint32_t)(k1 - k0) * (uint32_t)Lp * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(&bars[grp * 2 + (c & 1)], bytes);
+    bulk_g2s(mylat + (size_t)(c & 1) * kCtcChunk * Lp, lat_g + (size_t)t_lo * Lp, bytes, &bars[grp * 2 + (c & 1)]);
+  };
+  if (tid == 0) issue(0);
+
+  for (int c = 0; c < nchunks; ++c) {
+    if (tid == 0 && c + 1 < nchunks) issue(c + 1);
+    mbar_wait_or_trap(&bars[grp * 2 + (c & 1)], (uint32_t)((c >> 1) & 1));
+    const int k0 = c * kCtcChunk, k1 = min(Tb, k0 + kCtcChunk);
+    const int t_lo = (grp == 0) ? k0 : Tb - k1;
+    const float* chunk = mylat + (size_t)(c & 1) * kCtcChunk * Lp;
+    for (int k = k0; k < k1; ++k) {
+      const int t = (grp == 0) ? k : Tb - 1 - k;
+      const float* lrow = chunk + (size_t)(t - t_lo) * Lp;
+      const float* prev = my + (size_t)((k + 1) & 1) * Smax;
+      float* cur = my + (size_t)(k & 1) * Smax;
+      const bool renorm = ((k % kCtcRenorm) == kCtcRenorm - 1);
+      float vmax = kNegInf;
+      for (int s = tid; s < S; s += G) {
+        const float lp = lrow[(s & 1) ? (s >> 1) + 1 : 0];
+        float v;
+        if (k == 0) {
+          v = kNegInf;
+          if (grp == 0) {
+            if (s <= 1) v = lp;
+          } else {
+            if (s >= S - 2) v = lp;
+          }
+        } else {
+          float a0 = prev[s], a1 = kNegInf, a2 = kNegInf;
+          if (grp == 0) {
+            if (s >= 1) a1 = prev[s - 1];
+            if ((s & 1) && s >= 3 && lab[s] != lab[s - 2]) a2 = prev[s - 2];
+          } else {
+            if (s + 1 < S) a1 = prev[s + 1];
+            if ((s & 1) && s + 2 < S && lab[s] != lab[s + 2]) a2 = prev[s + 2];
+          }
+          v = lse3(a0, a1, a2) + lp;
+        }
+        cur[s] = v;
+        vmax = fmaxf(vmax, v);
+        if (!renorm) out_lat[(size_t)t * Smax + s] = v;
+      }
+      if (renorm) {
+        vmax = warp_max(vmax);
+        if ((tid & 31) == 0) wmax[grp * 32 + (tid >> 5)] = vmax;
+        __syncthreads();
+        float m = kNegInf;
+        for (int w = 0; w < nwarps_g; ++w) m = fmaxf(m, wmax[grp * 32 + w]);
+        if (m == kNegInf) m = 0.f;  // every state impossible: nothing to rescale
+        for (int s = tid; s < S; s += G) {
+          const float v = cur[s] - m;
+          cur[s] = v;
+          out_lat[(size_t)t * Smax + s] = v;
+        }
+        offset += (double)m;
+      }
+      if (tid == 0) out_off[t] = offset;
+      __syncthreads();
+    }
   }
   if (threadIdx.x == 0) {
     const float* fin = bufs + (size_t)((Tb - 1) & 1) * Smax;  // alpha at t = Tb-1
-    const float ll = lse2(fin[S - 1], (S >= 2) ? fin[S - 2] : kNegInf);
+    const float l = lse2(fin[S - 1], (S >= 2) ? fin[S - 2] : kNegInf);
+    const double ll = (l == kNegInf) ? -INFINITY : offset + (double)l;
     ws.ll[b] = ll;
-    costs[b] = (ll == kNegInf) ? 0.f : -ll;
+    costs[b] = (l == kNegInf) ? 0.f : (float)(-ll);
   }
 }
 
@@ -253,8 +302,8 @@ ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, long 
     const long long gr = row0 + r;
     const int t = (int)(gr / B), b = (int)(gr % B);
     float* row = tile + (size_t)r * A;
-    const float ll = ws.ll[b];
-    if (t >= act_lens[b] || ll == kNegInf) {
+    const double ll = ws.ll[b];
+    if (t >= act_lens[b] || ll == -INFINITY) {
       for (int a = lane; a < A; a += 32) row[a] = 0.f;
       continue;
     }
@@ -266,13 +315,15 @@ ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, long 
     const int off = ws.offsets[b];
     const float* al = ws.alpha + bt * (size_t)Smax;
     const float* be = ws.beta + bt * (size_t)Smax;
-    const float* lat = ws.lat + bt * (size_t)(Lmax + 1);
+    const float* lat = ws.lat + bt * (size_t)lat_stride(Lmax);
+    // alpha and beta are stored renormalised: fold both float64 offsets and the log-likelihood into one O(1) term
+    const float shift = (float)(ws.offa[bt] + ws.offb[bt] - ll);
     float blank_occ = 0.f;
     for (int s = lane; s < S; s += 32) {
       const float lp = lat[(s & 1) ? (s >> 1) + 1 : 0];
       const float ab = al[s] + be[s];
       // beta carries the emission at t as well as alpha: remove one copy; -inf states contribute 0
-      const float g = (ab == kNegInf) ? 0.f : expf(ab - lp - ll);
+      const float g = (ab == kNegInf) ? 0.f : expf(ab - lp + shift);
       if (s & 1) gs[s >> 1] = g;
       else blank_occ += g;
     }
@@ -329,7 +380,7 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
   static const int32_t kDummy = 0;
   const int32_t* labels_safe = labels ? labels : &kDummy;  // never dereferenced when Lmax == 0
 
-  ctc_prep_kernel<<<1, 1024, 0, stream>>>(labels_safe, label_lens, B, Lmax, ws);
+  ctc_scan_kernel<<<1, 1024, 0, stream>>>(label_lens, B, Lmax, ws);
   VOCR_CHECK_LAUNCH();
 
   const long long n_rows = (long long)T * B;
@@ -355,7 +406,8 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
   {
     int G = ((Smax + 31) / 32) * 32;
     if (G > 512) G = 512;
-    const size_t smem3 = sizeof(int) * (size_t)Smax + sizeof(float) * 4 * (size_t)Smax;
+    const size_t smem3 = 32 + sizeof(float) * ((size_t)4 * kCtcChunk * lat_stride(Lmax) + 4 * (size_t)Smax + 64) +
+                         sizeof(int) * (size_t)Smax;
     if (smem3 > 48 * 1024) {
       VOCR_REQUIRE(smem3 <= 200 * 1024);
       if (cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3) !=
