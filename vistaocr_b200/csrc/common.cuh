@@ -65,6 +65,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a descriptor/size bug must surface as an error, never as a hung GPU box.
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t max_spins = (1u << 24)) {
+#pragma unroll 1
   for (uint32_t i = 0; i < max_spins; ++i)
     if (mbar_try_wait(bar, parity)) return true;
   return false;

@@ -21,15 +21,20 @@ namespace vocr {
 constexpr int kCtcThreads = 256;
 constexpr int kCtcWarps = kCtcThreads / 32;
 
-__device__ __forceinline__ float lse3(float a, float b, float c) {
+// The recursions run in the log2 domain: one MUFU.EX2 per exp, one MUFU.LG2 per log, no range-reduction code on
+// the T-long dependent chain.  Natural-log quantities are converted once per frame (lattice) / utterance (cost).
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr double kLn2 = 0.6931471805599453;
+
+__device__ __forceinline__ float lse3_2(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
   if (m == kNegInf) return kNegInf;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + __log2f(exp2f(a - m) + exp2f(b - m) + exp2f(c - m));
 }
-__device__ __forceinline__ float lse2(float a, float b) {
+__device__ __forceinline__ float lse2_2(float a, float b) {
   const float m = fmaxf(a, b);
   if (m == kNegInf) return kNegInf;
-  return m + logf(expf(a - m) + expf(b - m));
+  return m + __log2f(exp2f(a - m) + exp2f(b - m));
 }
 
 constexpr int kCtcChunk = 16;  // lattice frames staged per bulk copy in the recursion kernel
@@ -39,11 +44,11 @@ struct CtcWorkspace {
   int32_t* offsets;  // [B+1]
   int32_t* nxt;      // [sum L] next position with the same symbol, -1 if none
   int32_t* first;    // [sum L] 1 if no earlier position has the same symbol
-  double* ll;        // [B] log-likelihood (-inf = infeasible)
+  double* ll;        // [B] log2-likelihood (-inf = infeasible)
   double* offa;      // [B*T] cumulative renormalisation offset of alpha at frame t
   double* offb;      // [B*T] same for beta
   float* lse;        // [B*T]
-  float* lat;        // [B*T*Lp] compact log-softmax lattice, Lp = round_up(Lmax+1, 4)
+  float* lat;        // [B*T*Lp] compact log2-softmax lattice, Lp = round_up(Lmax+1, 4)
   float* alpha;      // [B*T*Smax] renormalised alpha
   float* beta;       // [B*T*Smax] renormalised beta
 };
@@ -132,7 +137,7 @@ ctc_lse_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, 
     for (int j = lane; j <= L; j += 32) {
       int sym = (j == 0) ? 0 : labels[off + j - 1];
       sym = max(0, min(sym, A - 1));
-      lat[j] = row[sym] - lse;
+      lat[j] = (row[sym] - lse) * kLog2e;
     }
   }
 }
@@ -214,6 +219,22 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
     bulk_g2s(mylat + (size_t)(c & 1) * kCtcChunk * Lp, lat_g + (size_t)t_lo * Lp, bytes, &bars[grp * 2 + (c & 1)]);
   };
   if (tid == 0) issue(0);
+  // per-thread constants of state s = tid
+  const int dir = (grp == 0) ? -1 : 1;
+  const int li0 = (tid & 1) ? (tid >> 1) + 1 : 0;
+  bool n1 = false, n2 = false, init0 = false;
+  if (tid < S) {
+    if (grp == 0) {
+      n1 = tid >= 1;
+      n2 = (tid & 1) && tid >= 3 && lab[tid] != lab[tid - 2];
+      init0 = tid <= 1;
+    } else {
+      n1 = tid + 1 < S;
+      n2 = (tid & 1) && tid + 2 < S && lab[tid] != lab[tid + 2];
+      init0 = tid >= S - 2;
+    }
+  }
+  float own = kNegInf;
 
   for (int c = 0; c < nchunks; ++c) {
     if (tid == 0 && c + 1 < nchunks) issue(c + 1);
@@ -228,16 +249,27 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
       float* cur = my + (size_t)(k & 1) * Smax;
       const bool renorm = ((k % kCtcRenorm) == kCtcRenorm - 1);
       float vmax = kNegInf;
-      for (int s = tid; s < S; s += G) {
+      // state s = tid: neighbours, lattice slot and skip rule are per-thread constants, own value lives in a register
+      if (tid < S) {
+        const float lp = lrow[li0];
+        float v;
+        if (k == 0) {
+          v = init0 ? lp : kNegInf;
+        } else {
+          const float a1 = n1 ? prev[tid + dir] : kNegInf;
+          const float a2 = n2 ? prev[tid + 2 * dir] : kNegInf;
+          v = lse3_2(own, a1, a2) + lp;
+        }
+        own = v;
+        cur[tid] = v;
+        vmax = v;
+        if (!renorm) out_lat[(size_t)t * Smax + tid] = v;
+      }
+      for (int s = tid + G; s < S; s += G) {  // only when S > G (label length > 255)
         const float lp = lrow[(s & 1) ? (s >> 1) + 1 : 0];
         float v;
         if (k == 0) {
-          v = kNegInf;
-          if (grp == 0) {
-            if (s <= 1) v = lp;
-          } else {
-            if (s >= S - 2) v = lp;
-          }
+          v = ((grp == 0) ? (s <= 1) : (s >= S - 2)) ? lp : kNegInf;
         } else {
           float a0 = prev[s], a1 = kNegInf, a2 = kNegInf;
           if (grp == 0) {
@@ -247,7 +279,7 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
             if (s + 1 < S) a1 = prev[s + 1];
             if ((s & 1) && s + 2 < S && lab[s] != lab[s + 2]) a2 = prev[s + 2];
           }
-          v = lse3(a0, a1, a2) + lp;
+          v = lse3_2(a0, a1, a2) + lp;
         }
         cur[s] = v;
         vmax = fmaxf(vmax, v);
@@ -260,6 +292,7 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
         float m = kNegInf;
         for (int w = 0; w < nwarps_g; ++w) m = fmaxf(m, wmax[grp * 32 + w]);
         if (m == kNegInf) m = 0.f;  // every state impossible: nothing to rescale
+        own -= m;
         for (int s = tid; s < S; s += G) {
           const float v = cur[s] - m;
           cur[s] = v;
@@ -273,10 +306,10 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
   }
   if (threadIdx.x == 0) {
     const float* fin = bufs + (size_t)((Tb - 1) & 1) * Smax;  // alpha at t = Tb-1
-    const float l = lse2(fin[S - 1], (S >= 2) ? fin[S - 2] : kNegInf);
-    const double ll = (l == kNegInf) ? -INFINITY : offset + (double)l;
-    ws.ll[b] = ll;
-    costs[b] = (l == kNegInf) ? 0.f : (float)(-ll);
+    const float l = lse2_2(fin[S - 1], (S >= 2) ? fin[S - 2] : kNegInf);
+    const double ll2 = (l == kNegInf) ? -INFINITY : offset + (double)l;  // log2 p(labels | acts)
+    ws.ll[b] = ll2;
+    costs[b] = (l == kNegInf) ? 0.f : (float)(-ll2 * kLn2);
   }
 }
 
@@ -316,14 +349,14 @@ ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, long 
     const float* al = ws.alpha + bt * (size_t)Smax;
     const float* be = ws.beta + bt * (size_t)Smax;
     const float* lat = ws.lat + bt * (size_t)lat_stride(Lmax);
-    // alpha and beta are stored renormalised: fold both float64 offsets and the log-likelihood into one O(1) term
+    // alpha and beta are stored renormalised, in log2 units: fold both float64 offsets and the log-likelihood into one O(1) term
     const float shift = (float)(ws.offa[bt] + ws.offb[bt] - ll);
     float blank_occ = 0.f;
     for (int s = lane; s < S; s += 32) {
       const float lp = lat[(s & 1) ? (s >> 1) + 1 : 0];
       const float ab = al[s] + be[s];
       // beta carries the emission at t as well as alpha: remove one copy; -inf states contribute 0
-      const float g = (ab == kNegInf) ? 0.f : expf(ab - lp + shift);
+      const float g = (ab == kNegInf) ? 0.f : exp2f(ab - lp + shift);
       if (s & 1) gs[s >> 1] = g;
       else blank_occ += g;
     }
