@@ -1,0 +1,444 @@
+// 3x3 / pad 1 / stride 1 convolutions of the CNN feature extractor as implicit GEMM over NHWC fp32 activations
+// (reference cnnlstm.py:114-134,263-266 -> cuDNN): forward (+bias, + per-channel sum / sum-of-squares for the
+// BatchNorm that follows), data gradient (same kernel on flipped weights) and weight gradient (split-K over pixels).
+// The rapid-downsample stage (conv Cin->16 + ReLU + 2x2 max-pool, cnnlstm.py:114-121) is one fused direct kernel so
+// the full-resolution 16-channel intermediate is never written.
+//
+// GEMM views (P = B*H*W pixels, K index = (ky*3+kx)*Cin + ci):
+//   fwd   : Z[P,Cout]  = im2col(X)[P,9Cin]   * Wk[9Cin,Cout]
+//   dgrad : dX[P,Cin]  = im2col(dZ)[P,9Cout] * Wd[9Cout,Cin]      Wd[(ky,kx,co),ci] = W[co,ci,2-ky,2-kx]
+//   wgrad : dWk[9Cin,Cout] = im2col(X)^T[9Cin,P] * dZ[P,Cout]     split over P, reduced + re-laid-out afterwards
+#include "gemm_core.cuh"
+
+namespace vocr {
+
+// ---- im2col loader, contiguous along K (forward / dgrad): A(m = pixel, k..k+3) --------------------------------
+struct ConvALoad {
+  static constexpr bool kContigK = true;
+  const float* x;
+  int H, W, C;
+  long long P;
+  bool vec;  // C % 4 == 0 and base 16-B aligned: 4 consecutive k share a tap
+  struct State {
+    const float* base;  // &x[pixel, 0]
+    int y, xx, tap, ci;
+    bool valid;
+  };
+  __device__ __forceinline__ void init(State& st, int m, int k_first) const {
+    st.valid = m < P;
+    const int mm = st.valid ? m : 0;
+    st.xx = mm % W;
+    st.y = (mm / W) % H;
+    st.base = x + (size_t)mm * C;
+    st.tap = k_first / C;
+    st.ci = k_first - st.tap * C;
+  }
+  __device__ __forceinline__ float tap_elem(const State& st, int tap, int ci) const {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int yy = st.y + ky - 1, xc = st.xx + kx - 1;
+    if (yy < 0 || yy >= H || xc < 0 || xc >= W) return 0.f;
+    return __ldg(st.base + ((ky - 1) * W + (kx - 1)) * C + ci);
+  }
+  __device__ __forceinline__ float4 fetch(State& st, int k, int k_end) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (st.valid && k < k_end) {
+      if (vec) {
+        const int ky = st.tap / 3, kx = st.tap - ky * 3;
+        const int yy = st.y + ky - 1, xc = st.xx + kx - 1;
+        if (yy >= 0 && yy < H && xc >= 0 && xc < W)
+          v = __ldg(reinterpret_cast<const float4*>(st.base + ((ky - 1) * W + (kx - 1)) * C + st.ci));
+      } else {
+        int tap = st.tap, ci = st.ci;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (k + j < k_end) r[j] = tap_elem(st, tap, ci);
+          if (++ci == C) {
+            ci = 0;
+            ++tap;
+          }
+        }
+        v = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    st.ci += kGemmBK;
+    while (st.ci >= C) {
+      st.ci -= C;
+      ++st.tap;
+    }
+    return v;
+  }
+};
+
+// ---- im2col loader, contiguous along M (wgrad): A(m..m+3 = (tap,ci..ci+3), k = pixel) --------------------------
+struct ConvATLoad {
+  static constexpr bool kContigK = false;
+  const float* x;
+  int H, W, C, M;  // M = 9*C
+  bool vec;
+  struct State {
+    int m, tap, ci;  // first of the 4 rows
+    int y, xx;       // coordinates of the current pixel
+    long long p;
+  };
+  __device__ __forceinline__ void init(State& st, int m, int k_first) const {
+    st.m = m;
+    st.tap = m / C;
+    st.ci = m - st.tap * C;
+    st.p = k_first;
+    st.xx = k_first % W;
+    st.y = (k_first / W) % H;
+  }
+  __device__ __forceinline__ float elem(const State& st, int tap, int ci) const {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int yy = st.y + ky - 1, xc = st.xx + kx - 1;
+    if (yy < 0 || yy >= H || xc < 0 || xc >= W) return 0.f;
+    return __ldg(x + (size_t)(st.p + (ky - 1) * W + (kx - 1)) * C + ci);
+  }
+  __device__ __forceinline__ float4 fetch(State& st, int k, int k_end) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < k_end && st.m < M) {
+      if (vec) {
+        const int ky = st.tap / 3, kx = st.tap - ky * 3;
+        const int yy = st.y + ky - 1, xc = st.xx + kx - 1;
+        if (yy >= 0 && yy < H && xc >= 0 && xc < W)
+          v = __ldg(reinterpret_cast<const float4*>(x + (size_t)(st.p + (ky - 1) * W + (kx - 1)) * C + st.ci));
+      } else {
+        int tap = st.tap, ci = st.ci;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (st.m + j < M) r[j] = elem(st, tap, ci);
+          if (++ci == C) {
+            ci = 0;
+            ++tap;
+          }
+        }
+        v = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    st.p += kGemmBK;
+    st.xx += kGemmBK;
+    while (st.xx >= W) {
+      st.xx -= W;
+      if (++st.y == H) st.y = 0;
+    }
+    return v;
+  }
+};
+
+// ---- forward epilogue: z = acc + bias, optional per-channel sum / sum of squares (for BatchNorm) -------------------
+template <int BN>
+struct ConvFwdEpilogue {
+  float* z;
+  long long P;
+  int N;
+  const float* bias;
+  double* stats;  // [2*N] or nullptr
+  float* s_sum;   // shared [BN], s_sq shared [BN] (zeroed by the kernel)
+  float* s_sq;
+  int n0;
+  float cs[4 * (BN / 64)], cq[4 * (BN / 64)];
+  __device__ __forceinline__ void begin() {
+#pragma unroll
+    for (int j = 0; j < 4 * (BN / 64); ++j) cs[j] = cq[j] = 0.f;
+  }
+  __device__ __forceinline__ void operator()(int m, int n, float4 v, int j) {
+    if (m >= P || n >= N) return;
+    float r[4] = {v.x, v.y, v.z, v.w};
+    float* q = z + (size_t)m * N + n;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (n + c < N) {
+        if (bias) r[c] += __ldg(bias + n + c);
+        cs[4 * j + c] += r[c];
+        cq[4 * j + c] = fmaf(r[c], r[c], cq[4 * j + c]);
+      }
+    }
+    if ((N & 3) == 0) {
+      *reinterpret_cast<float4*>(q) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (n + c < N) q[c] = r[c];
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (!stats) return;
+    const int tx = threadIdx.x & 15;
+#pragma unroll
+    for (int j = 0; j < BN / 64; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = j * 64 + tx * 4 + c;
+        atomicAdd(&s_sum[col], cs[4 * j + c]);
+        atomicAdd(&s_sq[col], cq[4 * j + c]);
+      }
+    __syncthreads();
+    for (int col = threadIdx.x; col < BN; col += kGemmThreads) {
+      const int n = n0 + col;
+      if (n < N) {
+        atomicAdd(&stats[n], (double)s_sum[col]);
+        atomicAdd(&stats[N + n], (double)s_sq[col]);
+      }
+    }
+  }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads)
+conv3x3_fwd_kernel(ConvALoad la, BLoadContigN lb, float* z, const float* bias, double* stats, int N) {
+  __shared__ float s_sum[BN], s_sq[BN];
+  for (int i = threadIdx.x; i < BN; i += kGemmThreads) s_sum[i] = s_sq[i] = 0.f;
+  ConvFwdEpilogue<BN> ep;
+  ep.z = z; ep.P = la.P; ep.N = N; ep.bias = bias; ep.stats = stats; ep.s_sum = s_sum; ep.s_sq = s_sq;
+  ep.n0 = blockIdx.x * BN;
+  ep.begin();
+  // gemm_tile's first __syncthreads orders the zeroing above before any shared atomic
+  gemm_tile<BN>(la, lb, ep, blockIdx.y * kGemmBM, blockIdx.x * BN, 0, 9 * la.C);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads)
+conv3x3_wgrad_kernel(ConvATLoad la, BLoadContigN lb, float* partial, int M, int N, long long P,
+                     long long k_chunk) {
+  const long long k0 = (long long)blockIdx.z * k_chunk;
+  const long long k1 = min(P, k0 + k_chunk);
+  DenseEpilogue ep{partial + (size_t)blockIdx.z * M * N, M, N, N, nullptr, false, false, (N & 3) == 0};
+  gemm_tile<BN>(la, lb, ep, blockIdx.y * kGemmBM, blockIdx.x * BN, (int)k0, (int)k1);
+}
+
+// sum split-K partials [S][9*Cin][Cout] and write the PyTorch layout dW[Cout][Cin][3][3]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cin, int Cout, float* __restrict__ dw) {
+  const int total = 9 * Cin * Cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    // idx enumerates the OUTPUT (co, ci, tap) so the write is coalesced
+    const int tap = idx % 9;
+    const int ci = (idx / 9) % Cin;
+    const int co = idx / (9 * Cin);
+    const size_t src = (size_t)(tap * Cin + ci) * Cout + co;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + src];
+    dw[idx] = s;
+  }
+}
+
+// W[Cout][Cin][3][3] -> Wk[(ky,kx,ci)][co]  and  Wd[(ky,kx,co)][ci] = W[co][ci][2-ky][2-kx]
+__global__ void __launch_bounds__(256)
+conv_weight_layout_kernel(const float* __restrict__ w, int Cin, int Cout, float* __restrict__ wk,
+                          float* __restrict__ wd) {
+  const int total = 9 * Cin * Cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int tap = idx % 9;
+    const int ci = (idx / 9) % Cin;
+    const int co = idx / (9 * Cin);
+    const float v = w[idx];
+    if (wk) wk[(size_t)(tap * Cin + ci) * Cout + co] = v;
+    if (wd) wd[(size_t)((8 - tap) * Cout + co) * Cin + ci] = v;
+  }
+}
+
+// ---- rapid-downsample stage: conv3x3(Cin->16)+bias -> ReLU -> maxpool 2x2/2, fused, direct ----------------------
+// One thread = one pooled pixel x 4 output channels.  wk: [9*Cin][16].  arg (uint8, optional): which of the 4 window
+// positions won (first max in (dy,dx) scan order, like ATen max_pool2d), for the backward pass.
+constexpr int kRdsCout = 16;
+__global__ void __launch_bounds__(256)
+rds_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
+               float* __restrict__ y, uint8_t* __restrict__ arg, int B, int H, int W, int Cin) {
+  extern __shared__ float s_w[];  // [9*Cin][16]
+  for (int i = threadIdx.x; i < 9 * Cin * kRdsCout; i += blockDim.x) s_w[i] = wk[i];
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * 4;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cq = (int)(gid & 3);
+  const long long pp = gid >> 2;
+  const int xo = (int)(pp % Wo);
+  const int yo = (int)((pp / Wo) % Ho);
+  const int b = (int)(pp / ((long long)Wo * Ho));
+  float acc[4][4];  // [window position][channel]
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[p][c] = bias[cq * 4 + c];
+  const int y0 = yo * 2 - 1, x0 = xo * 2 - 1;  // top-left of the 4x4 input patch
+  const float* xb = x + (size_t)b * H * W * Cin;
+  for (int ci = 0; ci < Cin; ++ci) {
+    float patch[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int yy = y0 + r, xc = x0 + c;
+        patch[r][c] = (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(xb + ((size_t)yy * W + xc) * Cin + ci) : 0.f;
+      }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[((ky * 3 + kx) * Cin + ci) * kRdsCout + cq * 4]);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float v = patch[(p >> 1) + ky][(p & 1) + kx];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[p][c] = fmaf(v, wv[c], acc[p][c]);
+        }
+      }
+  }
+  float out[4];
+  uint32_t amask = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float best = fmaxf(acc[0][c], 0.f);
+    int bi = 0;
+#pragma unroll
+    for (int p = 1; p < 4; ++p) {
+      const float v = fmaxf(acc[p][c], 0.f);
+      if (v > best || v != v) {
+        best = v;
+        bi = p;
+      }
+    }
+    out[c] = best;
+    amask |= (uint32_t)bi << (8 * c);
+  }
+  const size_t o = (size_t)pp * kRdsCout + cq * 4;
+  *reinterpret_cast<float4*>(y + o) = make_float4(out[0], out[1], out[2], out[3]);
+  if (arg) *reinterpret_cast<uint32_t*>(arg + o) = amask;
+}
+
+// backward of ReLU + maxpool: scatter dy to the winning pre-activation position, dense dpre[B,H,W,16]
+// (positions that lost, and winners whose pooled value is 0 (ReLU inactive), get 0).
+__global__ void __launch_bounds__(256)
+rds_unpool_kernel(const float* __restrict__ dy, const float* __restrict__ y, const uint8_t* __restrict__ arg,
+                  float* __restrict__ dpre, int B, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * H * W * 4;  // one thread per (full-res pixel, channel quad)
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cq = (int)(gid & 3);
+  const long long pp = gid >> 2;
+  const int xc = (int)(pp % W);
+  const int yy = (int)((pp / W) % H);
+  const int b = (int)(pp / ((long long)W * H));
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int yo = yy >> 1, xo = xc >> 1;
+  if (yo < Ho && xo < Wo) {
+    const size_t o = (((size_t)b * Ho + yo) * Wo + xo) * kRdsCout + cq * 4;
+    const uint32_t am = *reinterpret_cast<const uint32_t*>(arg + o);
+    const float4 d = *reinterpret_cast<const float4*>(dy + o);
+    const float4 v = *reinterpret_cast<const float4*>(y + o);
+    const uint32_t mine = (uint32_t)((yy & 1) * 2 + (xc & 1));
+    if (((am >> 0) & 0xff) == mine && v.x > 0.f) g.x = d.x;
+    if (((am >> 8) & 0xff) == mine && v.y > 0.f) g.y = d.y;
+    if (((am >> 16) & 0xff) == mine && v.z > 0.f) g.z = d.z;
+    if (((am >> 24) & 0xff) == mine && v.w > 0.f) g.w = d.w;
+  }
+  *reinterpret_cast<float4*>(dpre + (size_t)pp * kRdsCout + cq * 4) = g;
+}
+
+}  // namespace vocr
+
+using namespace vocr;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int vocr_conv_weight_layout_f32(const float* w, int Cin, int Cout, float* wk, float* wd,
+                                           vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(w && Cin > 0 && Cout > 0 && (wk || wd));
+  const int total = 9 * Cin * Cout;
+  conv_weight_layout_kernel<<<min(ceil_div(total, 256), 4 * kNumSMs), 256, 0, stream>>>(w, Cin, Cout, wk, wd);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// x [B,H,W,Cin] NHWC, wk [9*Cin,Cout], z [B,H,W,Cout]; stats (optional) double[2*Cout] is ACCUMULATED into.
+extern "C" int vocr_conv3x3_fwd_f32(const float* x, const float* wk, const float* bias, float* z, int B, int H,
+                                    int W, int Cin, int Cout, double* stats, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
+  const long long P = (long long)B * H * W;
+  if (P == 0) return VOCR_OK;
+  VOCR_REQUIRE(x && wk && z && P < (1ll << 31) - 256);
+  ConvALoad la;
+  la.x = x; la.H = H; la.W = W; la.C = Cin; la.P = P; la.vec = (Cin % 4 == 0) && aligned16(x);
+  BLoadContigN lb;
+  lb.p = wk; lb.cols = Cout; lb.ld = Cout; lb.vec = (Cout % 4 == 0) && aligned16(wk);
+  if (Cout <= 64) {
+    dim3 grid(ceil_div(Cout, 64), (unsigned)ceil_div64(P, kGemmBM));
+    conv3x3_fwd_kernel<64><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, Cout);
+  } else {
+    dim3 grid(ceil_div(Cout, 128), (unsigned)ceil_div64(P, kGemmBM));
+    conv3x3_fwd_kernel<128><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, Cout);
+  }
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+extern "C" size_t vocr_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout) {
+  // generous upper bound on split count (see below)
+  return sizeof(float) * (size_t)9 * Cin * Cout * 64 + 256;
+}
+
+// dw [Cout,Cin,3,3] (PyTorch layout) = sum over pixels of im2col(x)^T dz.  x [B,H,W,Cin], dz [B,H,W,Cout].
+extern "C" int vocr_conv3x3_wgrad_f32(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin,
+                                      int Cout, void* workspace, size_t workspace_bytes, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dw && workspace);
+  const long long P = (long long)B * H * W;
+  VOCR_REQUIRE(P < (1ll << 31) - 256);
+  const int M = 9 * Cin, N = Cout;
+  if (P == 0) {
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * M * N, stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+    return VOCR_OK;
+  }
+  VOCR_REQUIRE(x && dz);
+  const int bn = (N <= 64) ? 64 : 128;
+  const int tiles = ceil_div(M, kGemmBM) * ceil_div(N, bn);
+  int splits = max(1, min(64, (2 * kNumSMs + tiles - 1) / tiles));
+  long long k_chunk = ceil_div64(P, splits);
+  k_chunk = ceil_div64(k_chunk, kGemmBK) * kGemmBK;
+  splits = (int)ceil_div64(P, k_chunk);
+  VOCR_REQUIRE(sizeof(float) * (size_t)M * N * splits <= workspace_bytes);
+  float* partial = static_cast<float*>(workspace);
+  ConvATLoad la;
+  la.x = x; la.H = H; la.W = W; la.C = Cin; la.M = M; la.vec = (Cin % 4 == 0) && aligned16(x);
+  BLoadContigN lb;
+  lb.p = dz; lb.cols = N; lb.ld = N; lb.vec = (N % 4 == 0) && aligned16(dz);
+  dim3 grid(ceil_div(N, bn), ceil_div(M, kGemmBM), splits);
+  if (bn == 64) conv3x3_wgrad_kernel<64><<<grid, kGemmThreads, 0, stream>>>(la, lb, partial, M, N, P, k_chunk);
+  else conv3x3_wgrad_kernel<128><<<grid, kGemmThreads, 0, stream>>>(la, lb, partial, M, N, P, k_chunk);
+  VOCR_CHECK_LAUNCH();
+  wgrad_reduce_kernel<<<min(ceil_div(M * N, 256), 4 * kNumSMs), 256, 0, stream>>>(partial, splits, Cin, Cout, dw);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+extern "C" int vocr_rds_fwd_f32(const float* x, const float* wk, const float* bias, float* y, uint8_t* arg, int B,
+                                int H, int W, int Cin, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H >= 2 && W >= 2 && Cin > 0 && Cin <= 64);
+  const long long total = (long long)B * (H / 2) * (W / 2) * 4;
+  if (total == 0) return VOCR_OK;
+  VOCR_REQUIRE(x && wk && bias && y && aligned16(y));
+  const size_t smem = sizeof(float) * 9 * Cin * kRdsCout;
+  rds_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, smem, stream>>>(x, wk, bias, y, arg, B, H, W, Cin);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+extern "C" int vocr_rds_unpool_f32(const float* dy, const float* y, const uint8_t* arg, float* dpre, int B, int H,
+                                   int W, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H >= 2 && W >= 2);
+  const long long total = (long long)B * H * W * 4;
+  if (total == 0) return VOCR_OK;
+  VOCR_REQUIRE(dy && y && arg && dpre);
+  rds_unpool_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(dy, y, arg, dpre, B, H, W);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}

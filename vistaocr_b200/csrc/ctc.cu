@@ -4,7 +4,8 @@
 //   1. ctc_scan_kernel        label offsets (exclusive scan of label_lens)
 //   2. ctc_lse_lattice_kernel streaming pass #1 over acts: row log-sum-exp (warp-shuffle max/sum) and the compact
 //                             log-softmax lattice  lat[b][t][0]=blank, lat[b][t][1+j]=label j   (L+1 floats/frame)
-//   3. ctc_alpha_beta_kernel  one CTA per utterance; an alpha warp-group walks t forward while a beta warp-group
+//   3. ctc_ab_warp_kernel     (L <= 191; ctc_alpha_beta_kernel, a multi-warp shared-memory form, beyond that)
+//                             one CTA per utterance; an alpha warp walks t forward while a beta warp
 //                             walks t backward CONCURRENTLY over the blank-extended lattice (S=2L+1 states),
 //                             one __syncthreads per time step for both; the lattice is streamed through shared
 //                             memory by bulk async copies; alpha/beta are renormalised every 8 steps (float64
@@ -313,6 +314,197 @@ __global__ void ctc_alpha_beta_kernel(const int32_t* __restrict__ labels, const 
   }
 }
 
+// ---- 3b. alpha / beta recursions, one WARP per direction, state in registers, warp shuffles ------------------------
+// The workhorse for label lengths up to 32*Q-1 (Q <= 6 -> L <= 191).  Lane i owns Q consecutive label positions
+// j = i*Q .. i*Q+Q-1, i.e. the state pairs (blank 2j, label 2j+1) of the blank-extended labelling, in registers.
+// A step needs exactly one remote value per lane - the previous lane's last label state - fetched with one
+// __shfl_up: no shared-memory exchange and no block barrier on the T-long dependent chain.  The beta recursion is
+// the alpha recursion of the REVERSED labelling walked backwards in time (same code, mirrored output index), so
+// warp 0 (alpha) and warp 1 (beta) never synchronise with each other.  The compact lattice is streamed through
+// shared memory with 1-D bulk async copies, double buffered per warp.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log2(2^a + 2^b) and log2(2^a + 2^b + 2^c); -inf safe (ex2(-inf) = 0, and an all--inf input returns -inf)
+__device__ __forceinline__ float lse2_w(float a, float b) {
+  const float m = fmaxf(a, b);
+  const float r = m + lg2_fast(ex2_fast(a - m) + ex2_fast(b - m));
+  return (m == kNegInf) ? kNegInf : r;
+}
+__device__ __forceinline__ float lse3_w(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float r = m + lg2_fast(ex2_fast(a - m) + ex2_fast(b - m) + ex2_fast(c - m));
+  return (m == kNegInf) ? kNegInf : r;
+}
+
+template <int Q>
+__global__ void __launch_bounds__(64)
+ctc_ab_warp_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens,
+                   const int32_t* __restrict__ act_lens, int T, int B, int A, int Lmax, CtcWorkspace ws,
+                   float* __restrict__ costs) {
+  extern __shared__ __align__(128) unsigned char abw_smem[];
+  const int Smax = 2 * Lmax + 1;
+  const int Lp = lat_stride(Lmax);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(abw_smem);   // [2 dir][2 buf]
+  float* latbuf = reinterpret_cast<float*>(abw_smem + 32);  // [2][2][kCtcChunk*Lp]
+  int* lab = reinterpret_cast<int*>(latbuf + (size_t)4 * kCtcChunk * Lp);  // [Lmax]
+  const int b = blockIdx.x;
+  const int L = max(0, min(label_lens[b], Lmax));
+  const int S = 2 * L + 1;
+  const int Tb = max(0, min(act_lens[b], T));
+  const int dirn = threadIdx.x >> 5;  // 0 alpha, 1 beta
+  const int lane = threadIdx.x & 31;
+  const int off = ws.offsets[b];
+  for (int j = threadIdx.x; j < L; j += blockDim.x) lab[j] = max(0, min(labels[off + j], A - 1));
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {  // duplicate-symbol chains for the gradient kernel
+    const int sym = lab[j];
+    int nx = -1, fi = 1;
+    for (int q = j + 1; q < L; ++q)
+      if (lab[q] == sym) {
+        nx = q;
+        break;
+      }
+    for (int q = 0; q < j; ++q)
+      if (lab[q] == sym) {
+        fi = 0;
+        break;
+      }
+    ws.nxt[off + j] = nx;
+    ws.first[off + j] = fi;
+  }
+  if (Tb == 0) {
+    if (threadIdx.x == 0) {
+      ws.ll[b] = (L == 0) ? 0.0 : -INFINITY;
+      costs[b] = 0.f;
+    }
+    return;
+  }
+  // per-lane constants.  Position j (in THIS direction's order) carries a blank state and, if j < L, a label state.
+  bool has_blank[Q], has_label[Q], skip[Q];
+  int slot[Q], oblank[Q], olabel[Q];
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    const int j = lane * Q + i;
+    has_blank[i] = j <= L;
+    has_label[i] = j < L;
+    const int jo = (dirn == 0) ? j : L - 1 - j;  // position in the original labelling
+    slot[i] = has_label[i] ? 1 + jo : 0;
+    int sym = 0, symp = -1;
+    if (has_label[i]) {
+      sym = lab[jo];
+      if (j >= 1) symp = lab[(dirn == 0) ? jo - 1 : jo + 1];
+    }
+    skip[i] = has_label[i] && j >= 1 && sym != symp;
+    oblank[i] = (dirn == 0) ? 2 * j : S - 1 - 2 * j;
+    olabel[i] = (dirn == 0) ? 2 * j + 1 : S - 2 - 2 * j;
+  }
+  float* mylat = latbuf + (size_t)dirn * 2 * kCtcChunk * Lp;
+  float* out_lat = (dirn == 0 ? ws.alpha : ws.beta) + (size_t)b * T * Smax;
+  double* out_off = (dirn == 0 ? ws.offa : ws.offb) + (size_t)b * T;
+  const float* lat_g = ws.lat + (size_t)b * T * Lp;
+  const int nchunks = ceil_div(Tb, kCtcChunk);
+  double offset = 0.0;
+  float bl[Q], lb[Q];
+#pragma unroll
+  for (int i = 0; i < Q; ++i) bl[i] = lb[i] = kNegInf;
+
+  auto issue = [&](int c) {  // lane 0 of each warp
+    const int k0 = c * kCtcChunk, k1 = min(Tb, k0 + kCtcChunk);
+    const int t_lo = (dirn == 0) ? k0 : Tb - k1;
+    const uint32_t bytes = (uint32_t)(k1 - k0) * (uint32_t)Lp * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(&bars[dirn * 2 + (c & 1)], bytes);
+    bulk_g2s(mylat + (size_t)(c & 1) * kCtcChunk * Lp, lat_g + (size_t)t_lo * Lp, bytes, &bars[dirn * 2 + (c & 1)]);
+  };
+  if (lane == 0) issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    __syncwarp();  // every lane is done reading buffer (c+1)&1 (chunk c-1) before it is refilled
+    if (lane == 0 && c + 1 < nchunks) issue(c + 1);
+    mbar_wait_or_trap(&bars[dirn * 2 + (c & 1)], (uint32_t)((c >> 1) & 1));
+    const int k0 = c * kCtcChunk, k1 = min(Tb, k0 + kCtcChunk);
+    const int t_lo = (dirn == 0) ? k0 : Tb - k1;
+    const float* chunk = mylat + (size_t)(c & 1) * kCtcChunk * Lp;
+    for (int k = k0; k < k1; ++k) {
+      const int t = (dirn == 0) ? k : Tb - 1 - k;
+      const float* lrow = chunk + (size_t)(t - t_lo) * Lp;
+      const float lpb = lrow[0];
+      float lpl[Q];
+#pragma unroll
+      for (int i = 0; i < Q; ++i) lpl[i] = lrow[slot[i]];
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+          const int j = lane * Q + i;
+          bl[i] = (j == 0) ? lpb : kNegInf;
+          lb[i] = (j == 0 && has_label[i]) ? lpl[i] : kNegInf;
+        }
+      } else {
+        float pl = __shfl_up_sync(0xffffffffu, lb[Q - 1], 1);  // previous lane's last label state
+        if (lane == 0) pl = kNegInf;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+          const float nb = lse2_w(bl[i], pl) + lpb;
+          const float nl = lse3_w(lb[i], bl[i], skip[i] ? pl : kNegInf) + lpl[i];
+          pl = lb[i];  // old label state of this position feeds the next position
+          bl[i] = has_blank[i] ? nb : kNegInf;
+          lb[i] = has_label[i] ? nl : kNegInf;
+        }
+      }
+      if ((k % kCtcRenorm) == kCtcRenorm - 1) {
+        float m = kNegInf;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) m = fmaxf(m, fmaxf(bl[i], lb[i]));
+        m = warp_max(m);
+        if (m != kNegInf) {
+#pragma unroll
+          for (int i = 0; i < Q; ++i) {
+            bl[i] -= m;
+            lb[i] -= m;
+          }
+          offset += (double)m;
+        }
+      }
+      float* orow = out_lat + (size_t)t * Smax;
+#pragma unroll
+      for (int i = 0; i < Q; ++i) {
+        if (has_blank[i]) orow[oblank[i]] = bl[i];
+        if (has_label[i]) orow[olabel[i]] = lb[i];
+      }
+      if (lane == 0) out_off[t] = offset;
+    }
+  }
+  if (dirn == 0) {
+    // alpha_{Tb-1}(S-1) is the blank of position L, alpha_{Tb-1}(S-2) the label of position L-1
+    float fb = kNegInf, fl = kNegInf;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const int j = lane * Q + i;
+      if (j == L) fb = bl[i];
+      if (j == L - 1) fl = lb[i];
+    }
+    fb = warp_max(fb);
+    fl = warp_max(fl);
+    if (lane == 0) {
+      const float l = lse2_w(fb, fl);
+      const double ll2 = (l == kNegInf) ? -INFINITY : offset + (double)l;
+      ws.ll[b] = ll2;
+      costs[b] = (l == kNegInf) ? 0.f : (float)(-ll2 * kLn2);
+    }
+  }
+}
+
 // ---- 4. gradient ------------------------------------------------------------------------------------------
 // dynamic smem: 16 B mbarrier + tile + per-warp occupancy scratch kCtcWarps*Smax floats
 __global__ void __launch_bounds__(kCtcThreads)
@@ -436,7 +628,28 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
         acts, n_rows, T, B, A, rows_per_tile, base_aligned, labels_safe, label_lens, act_lens, Lmax, ws);
     VOCR_CHECK_LAUNCH();
   }
-  {
+  if (Lmax + 1 <= 32 * 6) {
+    const int Q = ceil_div(Lmax + 1, 32);
+    const size_t smem3 = 32 + sizeof(float) * (size_t)4 * kCtcChunk * lat_stride(Lmax) + sizeof(int) * (size_t)(Lmax + 1);
+#define VOCR_LAUNCH_ABW(q)                                                                                         \
+  case q:                                                                                                          \
+    if (smem3 > 48 * 1024 && cudaFuncSetAttribute(ctc_ab_warp_kernel<q>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  (int)smem3) != cudaSuccess)                                      \
+      return VOCR_EXECUTION_FAILED;                                                                                \
+    ctc_ab_warp_kernel<q><<<B, 64, smem3, stream>>>(labels_safe, label_lens, act_lens, T, B, A, Lmax, ws, costs);    \
+    break;
+    switch (Q) {
+      VOCR_LAUNCH_ABW(1)
+      VOCR_LAUNCH_ABW(2)
+      VOCR_LAUNCH_ABW(3)
+      VOCR_LAUNCH_ABW(4)
+      VOCR_LAUNCH_ABW(5)
+      VOCR_LAUNCH_ABW(6)
+      default: return VOCR_INVALID_VALUE;
+    }
+#undef VOCR_LAUNCH_ABW
+    VOCR_CHECK_LAUNCH();
+  } else {
     int G = ((Smax + 31) / 32) * 32;
     if (G > 512) G = 512;
     const size_t smem3 = 32 + sizeof(float) * ((size_t)4 * kCtcChunk * lat_stride(Lmax) + 4 * (size_t)Smax + 64) +

@@ -4,8 +4,11 @@
 // Operands are described by loader functors so that the same main loop serves row-major / transposed matrices and
 // the im2col gathers of conv3x3 forward, dgrad and wgrad.  A loader declares which logical dimension is contiguous
 // in memory and returns 4 consecutive elements along it (zero-filled out of bounds):
-//   ALoader::kContigK ? fetch(m, k) -> A(m, k..k+3)  :  fetch(m, k) -> A(m..m+3, k)
-//   BLoader::kContigK ? fetch(k, n) -> B(k..k+3, n)  :  fetch(k, n) -> B(k, n..n+3)
+//   ALoader::kContigK ? fetch(st, k) -> A(m, k..k+3)  :  fetch(st, k) -> A(m..m+3, k)
+//   BLoader::kContigK ? fetch(st, k) -> B(k..k+3, n)  :  fetch(st, k) -> B(k, n..n+3)
+// `st` is a per-thread State initialised once per tile with the thread's fixed coordinate (m or n) and its first k;
+// successive fetches advance k by kGemmBK, which lets the conv loaders track (tap, channel) or (image, row, column)
+// incrementally instead of dividing.
 // fp32 FFMA is the exact-parity path (north_star tolerance 1e-5 relative); the tcgen05 path lives in tc_gemm.cu.
 #pragma once
 #include "common.cuh"
@@ -37,29 +40,31 @@ __device__ __forceinline__ void gemm_tile(const ALoader& la, const BLoader& lb, 
     for (int j = 0; j < 4 * NB; ++j) acc[i][j] = 0.f;
 
   float4 ra[2], rb[BV];
+  typename ALoader::State sa[2];
+  typename BLoader::State sb[BV];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int v = tid + i * kGemmThreads;
+    if (ALoader::kContigK) la.init(sa[i], m0 + (v >> 2), k_begin + (v & 3) * 4);
+    else la.init(sa[i], m0 + (v & 31) * 4, k_begin + (v >> 5));
+  }
+#pragma unroll
+  for (int i = 0; i < BV; ++i) {
+    const int v = tid + i * kGemmThreads;
+    if (BLoader::kContigK) lb.init(sb[i], n0 + (v >> 2), k_begin + (v & 3) * 4);
+    else lb.init(sb[i], n0 + (v % (BN / 4)) * 4, k_begin + v / (BN / 4));
+  }
 
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int v = tid + i * kGemmThreads;
-      if (ALoader::kContigK) {
-        const int row = v >> 2, kq = (v & 3) * 4;
-        ra[i] = la.fetch(m0 + row, k0 + kq, k_end);
-      } else {
-        const int k = v >> 5, mq = (v & 31) * 4;
-        ra[i] = la.fetch(m0 + mq, k0 + k, k_end);
-      }
+      ra[i] = la.fetch(sa[i], ALoader::kContigK ? k0 + (v & 3) * 4 : k0 + (v >> 5), k_end);
     }
 #pragma unroll
     for (int i = 0; i < BV; ++i) {
       const int v = tid + i * kGemmThreads;
-      if (BLoader::kContigK) {
-        const int col = v >> 2, kq = (v & 3) * 4;
-        rb[i] = lb.fetch(k0 + kq, n0 + col, k_end);
-      } else {
-        const int k = v / (BN / 4), nq = (v % (BN / 4)) * 4;
-        rb[i] = lb.fetch(k0 + k, n0 + nq, k_end);
-      }
+      rb[i] = lb.fetch(sb[i], BLoader::kContigK ? k0 + (v & 3) * 4 : k0 + v / (BN / 4), k_end);
     }
   };
   auto stash = [&](int buf) {
@@ -125,9 +130,10 @@ __device__ __forceinline__ void gemm_tile(const ALoader& la, const BLoader& lb, 
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const int n = n0 + j * 64 + tx * 4;
-      ep(m, n, make_float4(acc[i][4 * j], acc[i][4 * j + 1], acc[i][4 * j + 2], acc[i][4 * j + 3]));
+      ep(m, n, make_float4(acc[i][4 * j], acc[i][4 * j + 1], acc[i][4 * j + 2], acc[i][4 * j + 3]), j);
     }
   }
+  ep.finish();
 }
 
 // ---- dense loaders ------------------------------------------------------------------------------------------
@@ -135,7 +141,8 @@ __device__ __forceinline__ void gemm_tile(const ALoader& la, const BLoader& lb, 
 struct DenseContigK {
   static constexpr bool kContigK = true;
   const float* p;
-  int rows, ld;      // rows = extent of the non-K dimension
+  long long rows;    // extent of the non-K dimension
+  int ld;
   bool vec;          // base 16-B aligned and ld % 4 == 0
   // A(m, k..k+3)  or, used as a B loader, B(k..k+3, n) with (k, n) argument order
   __device__ __forceinline__ float4 get(int r, int k, int k_end) const {
@@ -151,10 +158,14 @@ struct DenseContigK {
   }
 };
 struct ALoadContigK : DenseContigK {
-  __device__ __forceinline__ float4 fetch(int m, int k, int k_end) const { return get(m, k, k_end); }
+  typedef int State;
+  __device__ __forceinline__ void init(State& st, int m, int) const { st = m; }
+  __device__ __forceinline__ float4 fetch(State& st, int k, int k_end) const { return get(st, k, k_end); }
 };
 struct BLoadContigK : DenseContigK {
-  __device__ __forceinline__ float4 fetch(int k, int n, int k_end) const { return get(n, k, k_end); }
+  typedef int State;
+  __device__ __forceinline__ void init(State& st, int n, int) const { st = n; }
+  __device__ __forceinline__ float4 fetch(State& st, int k, int k_end) const { return get(st, k, k_end); }
 };
 // Row-major matrix whose contiguous dimension is NOT K (A given as [K,M], or B given as [K,N]).
 struct DenseContigMN {
@@ -162,7 +173,7 @@ struct DenseContigMN {
   const float* p;
   int cols, ld;  // cols = extent of the contiguous (M or N) dimension
   bool vec;
-  __device__ __forceinline__ float4 get(int k, int c, int k_end) const {
+  __device__ __forceinline__ float4 get(long long k, int c, long long k_end) const {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k >= k_end) return v;
     const float* q = p + (size_t)k * ld + c;
@@ -175,10 +186,14 @@ struct DenseContigMN {
   }
 };
 struct ALoadContigM : DenseContigMN {
-  __device__ __forceinline__ float4 fetch(int m, int k, int k_end) const { return get(k, m, k_end); }
+  typedef int State;
+  __device__ __forceinline__ void init(State& st, int m, int) const { st = m; }
+  __device__ __forceinline__ float4 fetch(State& st, int k, int k_end) const { return get(k, st, k_end); }
 };
 struct BLoadContigN : DenseContigMN {
-  __device__ __forceinline__ float4 fetch(int k, int n, int k_end) const { return get(k, n, k_end); }
+  typedef int State;
+  __device__ __forceinline__ void init(State& st, int n, int) const { st = n; }
+  __device__ __forceinline__ float4 fetch(State& st, int k, int k_end) const { return get(k, st, k_end); }
 };
 
 // ---- dense epilogue: C = [C +] acc [+ bias[n]] [relu] ---------------------------------------------------------
@@ -187,7 +202,8 @@ struct DenseEpilogue {
   int M, N, ldc;
   const float* bias;  // [N] or nullptr
   bool relu, accumulate, vec;
-  __device__ __forceinline__ void operator()(int m, int n, float4 v) const {
+  __device__ __forceinline__ void finish() const {}
+  __device__ __forceinline__ void operator()(int m, int n, float4 v, int) const {
     if (m >= M || n >= N) return;
     float r[4] = {v.x, v.y, v.z, v.w};
     float* q = c + (size_t)m * ldc + n;
