@@ -1,0 +1,250 @@
+// BatchNorm2d (+ReLU) over NHWC fp32 activations [P = B*H*W pixels, C channels] (reference cnnlstm.py:263-266:
+// nn.BatchNorm2d(eps 1e-5, momentum 0.1) + nn.ReLU).  The per-channel sum / sum of squares come out of the conv
+// epilogue (conv.cu) in float64; here: finalize (batch or running statistics -> scale/shift, running-stat update),
+// apply+ReLU (strided output so the last block can write the [T,B,h*C] sequence layout directly), and the backward
+// pass (masked reductions, then dz and the conv-bias gradient).  HBM-bound elementwise / reduction kernels: float4
+// along C, grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace vocr {
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps, int training,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    const double m = stats[c] / count;
+    double var = stats[C + c] / count - m * m;  // biased batch variance (used for normalisation)
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = (count > 1.0) ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = 1.0f / sqrtf(running_var[c] + eps);
+  }
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (save_mean) save_mean[c] = mean;
+  if (save_invstd) save_invstd[c] = invstd;
+}
+
+// a[b,y,x,c] (strided) = relu(z[p,c]*scale[c] + shift[c])
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                     float* __restrict__ a, long long P, int H, int W, int C4, long long sB, long long sH,
+                     long long sW) {
+  const long long total = P * C4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    const long long p = idx / C4;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(z) + idx);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+    float4 r;
+    r.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+    r.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+    r.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+    r.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+    *reinterpret_cast<float4*>(a + b * sB + y * sH + x * sW + (long long)c4 * 4) = r;
+  }
+}
+
+// Backward pass 1: per-channel  s1 = sum g,  s2 = sum g * xhat,  g = da * [z*scale+shift > 0],
+// xhat = (z - mean) * invstd.  block = 256 threads = (256/C4) pixel rows x C4 float4 columns.
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ z,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int H,
+                          int W, int C4, long long sB, long long sH, long long sW, long long rows_per_cta,
+                          double* __restrict__ red) {
+  extern __shared__ float s_red[];  // [rows][C4*8]
+  const int rows = 256 / C4;
+  const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+  const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p0 = (long long)blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
+  if (r < rows) {
+    for (long long p = p0 + r; p < p1; p += rows) {
+      const int x = (int)(p % W);
+      const int y = (int)((p / W) % H);
+      const long long b = p / ((long long)W * H);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(z) + p * C4 + c4);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(da + b * sB + y * sH + x * sW + (long long)c4 * 4));
+      const float g0 = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f;
+      const float g1 = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
+      const float g2 = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f;
+      const float g3 = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
+      s1[0] += g0; s1[1] += g1; s1[2] += g2; s1[3] += g3;
+      s2[0] = fmaf(g0, (v.x - mu.x) * is.x, s2[0]);
+      s2[1] = fmaf(g1, (v.y - mu.y) * is.y, s2[1]);
+      s2[2] = fmaf(g2, (v.z - mu.z) * is.z, s2[2]);
+      s2[3] = fmaf(g3, (v.w - mu.w) * is.w, s2[3]);
+    }
+  }
+  float* mine = s_red + (size_t)threadIdx.x * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mine[i] = s1[i];
+    mine[4 + i] = s2[i];
+  }
+  __syncthreads();
+  // first C4*8 threads... C4*8 may exceed 256 (C=256 -> 512): loop
+  const int C = C4 * 4;
+  for (int o = threadIdx.x; o < 2 * C; o += 256) {
+    const int which = o / C, c = o % C;  // which: 0 -> s1, 1 -> s2
+    double t = 0.0;
+    for (int rr = 0; rr < rows; ++rr) t += (double)s_red[((size_t)rr * C4 + (c >> 2)) * 8 + which * 4 + (c & 3)];
+    atomicAdd(&red[which * C + c], t);
+  }
+}
+
+// Backward pass 2: dz = scale * (g - s1/N - xhat * s2/N)  (training)  or  scale * g  (eval);  also sums dz per channel
+// (the gradient of the conv bias that precedes the BatchNorm) into red_bias (float64).
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const double* __restrict__ red, double inv_count,
+                         int training, long long P, int H, int W, int C4, long long sB, long long sH, long long sW,
+                         long long rows_per_cta, float* __restrict__ dz, double* __restrict__ red_bias) {
+  extern __shared__ float s_red[];  // [256][4]
+  const int rows = 256 / C4;
+  const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
+  const int C = C4 * 4;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+  const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
+  float m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (training) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      m1[i] = (float)(red[c4 * 4 + i] * inv_count);
+      m2[i] = (float)(red[C + c4 * 4 + i] * inv_count);
+    }
+  }
+  float sb[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p0 = (long long)blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
+  if (r < rows) {
+    for (long long p = p0 + r; p < p1; p += rows) {
+      const int x = (int)(p % W);
+      const int y = (int)((p / W) % H);
+      const long long b = p / ((long long)W * H);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(z) + p * C4 + c4);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(da + b * sB + y * sH + x * sW + (long long)c4 * 4));
+      const float g0 = fmaf(v.x, sc.x, sh.x) > 0.f ? d.x : 0.f;
+      const float g1 = fmaf(v.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
+      const float g2 = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f;
+      const float g3 = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
+      float4 o;
+      o.x = sc.x * (g0 - m1[0] - (v.x - mu.x) * is.x * m2[0]);
+      o.y = sc.y * (g1 - m1[1] - (v.y - mu.y) * is.y * m2[1]);
+      o.z = sc.z * (g2 - m1[2] - (v.z - mu.z) * is.z * m2[2]);
+      o.w = sc.w * (g3 - m1[3] - (v.w - mu.w) * is.w * m2[3]);
+      sb[0] += o.x; sb[1] += o.y; sb[2] += o.z; sb[3] += o.w;
+      *(reinterpret_cast<float4*>(dz) + p * C4 + c4) = o;
+    }
+  }
+  if (red_bias) {
+    float* mine = s_red + (size_t)threadIdx.x * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mine[i] = sb[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      double t = 0.0;
+      for (int rr = 0; rr < rows; ++rr) t += (double)s_red[((size_t)rr * C4 + (c >> 2)) * 4 + (c & 3)];
+      atomicAdd(&red_bias[c], t);
+    }
+  }
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+}  // namespace vocr
+
+using namespace vocr;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, float momentum, float eps,
+                                    int training, float* scale, float* shift, float* save_mean, float* save_invstd,
+                                    int C, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(C > 0 && gamma && beta && scale && shift);
+  VOCR_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var));
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, (double)count, gamma, beta, running_mean,
+                                                           running_var, momentum, eps, training, scale, shift,
+                                                           save_mean, save_invstd, C);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, int B, int H,
+                                      int W, int C, long long sB, long long sH, long long sW,
+                                      vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long P = (long long)B * H * W;
+  if (P == 0) return VOCR_OK;
+  VOCR_REQUIRE(z && scale && shift && a && C > 0 && C % 4 == 0);
+  VOCR_REQUIRE(aligned16(z) && aligned16(a) && aligned16(scale) && aligned16(shift));
+  VOCR_REQUIRE(sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
+  const long long total = P * (C / 4);
+  const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
+  bn_relu_apply_kernel<<<grid, 256, 0, stream>>>(z, scale, shift, a, P, H, W, C / 4, sB, sH, sW);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// red: double[2*C] (zeroed here), filled with s1 (= dbeta) and s2 (= dgamma); dz [P,C]; dgamma/dbeta/dbias fp32 [C].
+// red_ws: double[3*C] scratch.
+extern "C" int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float* scale, const float* shift,
+                                    const float* save_mean, const float* save_invstd, int training, int B, int H,
+                                    int W, int C, long long sB, long long sH, long long sW, float* dz,
+                                    float* dgamma, float* dbeta, float* dbias, double* red_ws,
+                                    vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long P = (long long)B * H * W;
+  VOCR_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && red_ws && dz && dgamma && dbeta);
+  if (cudaMemsetAsync(red_ws, 0, sizeof(double) * 3 * C, stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+  if (P > 0) {
+    VOCR_REQUIRE(da && z && scale && shift && save_mean && save_invstd);
+    VOCR_REQUIRE(aligned16(z) && aligned16(da) && aligned16(dz) && sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
+    const int C4 = C / 4;
+    const int rows = 256 / C4;
+    long long rows_per_cta = ceil_div64(P, (long long)kNumSMs * 4);
+    rows_per_cta = max((long long)rows * 8, ceil_div64(rows_per_cta, rows) * rows);
+    const int grid = (int)ceil_div64(P, rows_per_cta);
+    bn_relu_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 256 * 8, stream>>>(
+        da, z, scale, shift, save_mean, save_invstd, P, H, W, C4, sB, sH, sW, rows_per_cta, red_ws);
+    VOCR_CHECK_LAUNCH();
+    bn_relu_bwd_apply_kernel<<<grid, 256, sizeof(float) * 256 * 4, stream>>>(
+        da, z, scale, shift, save_mean, save_invstd, red_ws, 1.0 / (double)P, training, P, H, W, C4, sB, sH, sW,
+        rows_per_cta, dz, dbias ? red_ws + 2 * C : nullptr);
+    VOCR_CHECK_LAUNCH();
+  }
+  f64_to_f32_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(red_ws, dbeta, C);
+  f64_to_f32_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(red_ws + C, dgamma, C);
+  if (dbias) f64_to_f32_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(red_ws + 2 * C, dbias, C);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
