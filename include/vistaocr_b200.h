@@ -66,6 +66,98 @@ int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t* labels, co
                       const int32_t* act_lens, int T, int B, int A, int max_label_len, float* costs,
                       void* workspace, size_t workspace_bytes, vocr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense fp32 GEMM with fused epilogue.  Replaces the cuBLAS calls behind nn.Linear in bridge_layer / prob_layer
+ * (src/models/cnnlstm.py:143-146,152-154,278,294), the LSTM input projections (nn.LSTM, :148-149) and their
+ * backward GEMMs.  Row-major.  C[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[n]) (+ C if accumulate) (ReLU if relu).
+ *   transa = 0: A is [M,K] (lda >= K)   transa = 1: A is stored [K,M] (lda >= M)
+ *   transb = 0: B is [K,N] (ldb >= N)   transb = 1: B is stored [N,K] (ldb >= K)   (nn.Linear weight layout)
+ * vocr_colsum_f32: out[c] (+)= sum_r x[r*ld + c]  (bias gradients).
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                  float* C, int ldc, const float* bias, int relu, int accumulate, vocr_stream_t stream);
+int vocr_colsum_f32(const float* x, long long rows, int cols, int ld, float* out, int accumulate,
+                    vocr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CNN feature extractor, NHWC fp32.  Replaces cuDNN conv / ATen pooling / cuDNN BatchNorm behind
+ * CnnOcrModel.rapid_ds and .cnn (src/models/cnnlstm.py:114-134,263-266,270-271).
+ *
+ * vocr_conv_weight_layout_f32: W[Cout,Cin,3,3] (state_dict layout) -> wk[(ky,kx,ci),co] (forward) and/or
+ *   wd[(ky,kx,co),ci] = W[co,ci,2-ky,2-kx] (data gradient); either output may be NULL.
+ * vocr_conv3x3_fwd_f32: z[B,H,W,Cout] = conv3x3_pad1(x[B,H,W,Cin]; wk) + bias.  If stats != NULL the per-channel
+ *   sum and sum of squares of z are ACCUMULATED into stats[0:Cout], stats[Cout:2Cout] (float64; caller zeroes).
+ *   The data gradient is the same call with (x := dz, wk := wd, Cin/Cout swapped, bias = stats = NULL).
+ * vocr_conv3x3_wgrad_f32: dw[Cout,Cin,3,3] = sum over pixels (state_dict layout, deterministic split-K).
+ * vocr_rds_fwd_f32: rapid-downsample stage, y[B,H/2,W/2,16] = maxpool2x2(relu(conv3x3(x[B,H,W,Cin]; wk[9*Cin,16])
+ *   + bias)); arg (uint8 per output, may be NULL) records the winning window position for the backward pass.
+ * vocr_rds_unpool_f32: dpre[B,H,W,16] = gradient w.r.t. the conv output of that stage (zeros where the position
+ *   lost the max or ReLU was inactive); conv gradients then use vocr_conv3x3_wgrad_f32 / _fwd_f32.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_conv_weight_layout_f32(const float* w, int Cin, int Cout, float* wk, float* wd, vocr_stream_t stream);
+int vocr_conv3x3_fwd_f32(const float* x, const float* wk, const float* bias, float* z, int B, int H, int W, int Cin,
+                         int Cout, double* stats, vocr_stream_t stream);
+size_t vocr_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout);
+int vocr_conv3x3_wgrad_f32(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout,
+                           void* workspace, size_t workspace_bytes, vocr_stream_t stream);
+int vocr_rds_fwd_f32(const float* x, const float* wk, const float* bias, float* y, uint8_t* arg, int B, int H, int W,
+                     int Cin, vocr_stream_t stream);
+int vocr_rds_unpool_f32(const float* dy, const float* y, const uint8_t* arg, float* dpre, int B, int H, int W,
+                        vocr_stream_t stream);
+
+/* BatchNorm2d(eps, momentum) + ReLU (src/models/cnnlstm.py:263-266).
+ * vocr_bn_finalize_f32: training != 0: batch statistics from stats (see conv fwd) over `count` pixels, running
+ *   stats updated in place (unbiased variance); else running stats.  Emits scale = gamma*invstd,
+ *   shift = beta - mean*scale and (optionally) save_mean / save_invstd for the backward pass.
+ * vocr_bn_relu_apply_f32: a[b*sB + y*sH + x*sW + c] = relu(z[b,y,x,c]*scale[c] + shift[c])  (strides in elements,
+ *   c contiguous) - the last CNN block writes the [T,B,h*C] sequence layout directly (replaces the
+ *   permute+contiguous of cnnlstm.py:276).
+ * vocr_bn_relu_bwd_f32: da (same strided layout) -> dz[B,H,W,C], dgamma, dbeta, dbias (= sum dz, the gradient of
+ *   the conv bias in front of the BatchNorm; may be NULL).  red_ws: float64[3*C] scratch.
+ */
+int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, int training,
+                         float* scale, float* shift, float* save_mean, float* save_invstd, int C,
+                         vocr_stream_t stream);
+int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, int B, int H, int W,
+                           int C, long long sB, long long sH, long long sW, vocr_stream_t stream);
+int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float* scale, const float* shift,
+                         const float* save_mean, const float* save_invstd, int training, int B, int H, int W, int C,
+                         long long sB, long long sH, long long sW, float* dz, float* dgamma, float* dbeta,
+                         float* dbias, double* red_ws, vocr_stream_t stream);
+
+/* FractionalMaxPool2d(2, output_ratio=(0.5,0.7)) with explicit per-(sample,channel) samples[B,C,2]
+ * (src/models/cnnlstm.py:127,130; ATen interval rule, random in train AND eval).  idx (int32, may be NULL) keeps the
+ * flat input position h*W+w of each winner; backward scatter-adds dy through idx into dx (zeroed inside). */
+int vocr_fracpool_fwd_f32(const float* x, const float* samples, float* y, int32_t* idx, int B, int H, int W, int C,
+                          int Ho, int Wo, vocr_stream_t stream);
+int vocr_fracpool_bwd_f32(const float* dy, const int32_t* idx, float* dx, int B, int H, int W, int C, int Ho,
+                          int Wo, vocr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bidirectional LSTM layer recurrence (persistent cooperative kernels).  Replaces the cuDNN RNN behind
+ * nn.LSTM(bidirectional) on a packed sequence (src/models/cnnlstm.py:148-149,285-290).  PyTorch gate order i,f,g,o.
+ *   xproj [T,B,2,4H] = x W_ih^T + b_ih + b_hh for both directions (one vocr_gemm_f32);  whh [2,4H,H];
+ *   lens [B] int32 (device): sample b is processed for t < lens[b]; the reverse direction starts at lens[b]-1;
+ *   out [T,B,2H] (forward | reverse), zero for t >= lens[b];  Tmax = max(lens) <= T.
+ *   gates [T,B,2,4H] / cst [T,B,2,H]: activated gates and cell states saved for backward (NULL for inference).
+ * backward: dout [T,B,2H] -> dgates [T,B,2,4H] = gradient w.r.t. xproj (zero beyond lens); the weight / input
+ * gradients are GEMMs over dgates (see vistaocr_b200/ops.py).  H <= 512.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t vocr_bilstm_workspace_size(int B, int H, int backward);
+int vocr_bilstm_fwd_f32(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates,
+                        float* cst, int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes,
+                        vocr_stream_t stream);
+int vocr_bilstm_bwd_f32(const float* dout, const float* whh, const int32_t* lens, const float* gates,
+                        const float* cst, float* dgates, int T, int B, int H, int Tmax, void* workspace,
+                        size_t workspace_bytes, vocr_stream_t stream);
+
+/* Fused element-wise gradient clamp to [-clamp,clamp] + torch.optim.Adam update over a flat parameter buffer
+ * (src/train_cnn_lstm.py:143-149,363).  step >= 1; clamp <= 0 disables; grad_scale pre-multiplies the gradient. */
+int vocr_clamp_adam_f32(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, float clamp, float grad_scale,
+                        vocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,161 @@
+"""GPU parity of the whole path: CnnOcrModel forward (eval + train), CTC loss, backward, decode - against the golden
+fixtures generated from the reference (tests/golden/*.npz) and against the oracle restatement on fresh inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as M
+from oracle.decode_ref import decode_loop
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# fp32 bound on logits after 7 convs + LSTM stack: 1e-5 relative to the tensor's scale, plus a small absolute term
+RTOL, ATOL = 1e-5, 2e-6
+
+CONFIGS = {
+    "h30": dict(input_line_height=30, rds_line_height=30, lstm_input_dim=16, num_lstm_layers=2,
+                num_lstm_hidden_units=24, p_lstm_dropout=0.0),
+    "h60": dict(input_line_height=60, rds_line_height=30, lstm_input_dim=24, num_lstm_layers=3,
+                num_lstm_hidden_units=16, p_lstm_dropout=0.0),
+    "h120": dict(input_line_height=120, rds_line_height=30, lstm_input_dim=8, num_lstm_layers=1,
+                 num_lstm_hidden_units=8, p_lstm_dropout=0.0),
+}
+
+
+def _alphabet(n):
+    from vistaocr_b200 import Alphabet
+    return Alphabet(["<ctc-blank>"] + ["u%04x" % (0x61 + i) for i in range(n - 1)])
+
+
+def _model(hp, n_symbols, sd, cuda):
+    from vistaocr_b200 import CnnOcrModel
+    m = CnnOcrModel(alphabet=_alphabet(n_symbols), verbose=False, **hp)
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def _close(got, want, what, rtol=RTOL, atol=ATOL):
+    got = torch.as_tensor(got).detach().double().cpu()
+    want = torch.as_tensor(want).detach().double().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs().max().item()
+    bound = rtol * want.abs().max().item() + atol
+    assert err <= bound, "%s: max err %.3e > bound %.3e" % (what, err, bound)
+
+
+@pytest.mark.parametrize("name", ["h30", "h60", "h120"])
+def test_golden_from_reference(cuda, name):
+    """Same weights, inputs and pool samples as the reference run that produced the fixture."""
+    from vistaocr_b200 import CTCLoss
+    hp = CONFIGS[name]
+    z = np.load(os.path.join(GOLD, "model_%s.npz" % name))
+    A = int(z["n_symbols"])
+    sd = M.make_state_dict(hp, A, seed=int(z["seed"]))
+    model = _model(hp, A, sd, cuda)
+    x = torch.from_numpy(z["x"]).to(cuda)
+    widths = torch.from_numpy(z["widths"])
+    model.cnn[6]._random_samples = torch.from_numpy(z["u1"])
+    model.cnn[13]._random_samples = torch.from_numpy(z["u2"])
+    model.eval()
+    with torch.no_grad():
+        logits, lens = model(x, widths)
+    assert lens.dtype == torch.int32 and not lens.is_cuda and lens.tolist() == z["lens"].tolist()
+    _close(logits, z["eval_logits"], "eval logits")
+    assert model.decode_without_lm(logits, lens, uxxxx=True) == z["eval_hyp"].tolist()  # bit-exact transcripts
+    assert model.decode_without_lm(logits, lens, uxxxx=False) == z["eval_hyp_utf8"].tolist()
+    # padded frames carry exactly the prob-layer bias
+    for b in range(x.shape[0]):
+        if lens[b] < logits.shape[0]:
+            assert torch.equal(logits[lens[b]:, b], model.prob_layer[0].bias.expand(logits.shape[0] - lens[b], -1))
+    model.train()
+    logits, lens = model(x, widths)
+    _close(logits, z["train_logits"], "train logits", rtol=2e-5)
+    loss = CTCLoss()(logits, torch.from_numpy(z["labels"]), lens, torch.from_numpy(z["label_lens"]))
+    assert abs(loss.data[0].item() - float(z["train_loss"])) <= 2e-5 * float(z["train_loss"])
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k in z.files:
+        if k.startswith("grad."):
+            want = z[k]
+            if k.endswith("cnn.0.bias"):
+                continue
+            _close(named[k[5:]].grad, want, k, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(want).max()))
+        if k.startswith("after."):
+            _close(model.state_dict()[k[6:]], z[k], k)
+
+
+def test_fresh_batch_against_oracle(cuda):
+    """A lively model on a fresh ragged batch: logits vs the oracle in float64, greedy strings bit-exact vs the
+    oracle decode of OUR logits, all parameter gradients vs oracle autograd."""
+    from vistaocr_b200 import CTCLoss
+    hp = dict(input_line_height=30, rds_line_height=30, lstm_input_dim=32, num_lstm_layers=2,
+              num_lstm_hidden_units=40, p_lstm_dropout=0.0)
+    A = 31
+    sd = M.make_state_dict(hp, A, seed=5)
+    model = _model(hp, A, sd, cuda)
+    rng = np.random.default_rng(9)
+    x, widths, labels, label_lens = M.synth_batch(rng, 5, 30, 40, 160, A, 2, 10)
+    u1 = torch.from_numpy(rng.random((5, 64, 2)).astype(np.float32))
+    u2 = torch.from_numpy(rng.random((5, 128, 2)).astype(np.float32))
+    model.cnn[6]._random_samples, model.cnn[13]._random_samples = u1, u2
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    for k in sd64:
+        if sd64[k].is_floating_point():
+            sd64[k].requires_grad_(True)
+    model.train()
+    logits, lens = model(torch.from_numpy(x).to(cuda), torch.from_numpy(widths))
+    want, wlens = M.forward_ref(sd64, torch.from_numpy(x).double(), widths, hp, (u1, u2), training=True,
+                                bn_updates={}, use_nn_lstm=False)
+    assert lens.tolist() == wlens.tolist()
+    _close(logits, want, "logits vs float64 oracle", rtol=2e-5)
+    hyp = model.decode_without_lm(logits, lens, uxxxx=True)
+    assert hyp == decode_loop(logits.detach().cpu().numpy(), lens.numpy(), model.alphabet.idx_to_char, uxxxx=True)
+    loss = CTCLoss()(logits, torch.from_numpy(labels), lens, torch.from_numpy(label_lens))
+    wloss = M.ctc_sum_ref(want, labels, wlens, label_lens)
+    assert abs(loss.data[0].item() - wloss.item()) <= 2e-5 * abs(wloss.item())
+    loss.backward()
+    wloss.backward()
+    for k, p in model.named_parameters():
+        w = sd64[k].grad
+        if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
+            assert p.grad.abs().max().item() <= 1e-3  # mathematically zero (conv bias before train-mode BN)
+            continue
+        _close(p.grad, w, "grad " + k, rtol=2e-4, atol=1e-6)
+
+
+def test_train_step_with_fused_optimizer(cuda):
+    """train_step() (= the reference's train()) with ClampAdam moves the parameters like clamp + torch Adam on the
+    oracle's gradients."""
+    from vistaocr_b200 import ClampAdam, CTCLoss, train_step
+    hp = CONFIGS["h30"]
+    A = 13
+    sd = M.make_state_dict(hp, A, seed=21)
+    model = _model(hp, A, sd, cuda)
+    model.train()
+    rng = np.random.default_rng(3)
+    x, widths, labels, label_lens = M.synth_batch(rng, 4, 30, 30, 90, A, 1, 6)
+    u1 = torch.from_numpy(rng.random((4, 64, 2)).astype(np.float32))
+    u2 = torch.from_numpy(rng.random((4, 128, 2)).astype(np.float32))
+    model.cnn[6]._random_samples, model.cnn[13]._random_samples = u1, u2
+    opt = ClampAdam(model.parameters(), lr=1e-3)
+    batch = (torch.from_numpy(x), torch.from_numpy(labels), torch.from_numpy(widths), torch.from_numpy(label_lens), {})
+    loss = train_step(batch, model, CTCLoss(host_cost=False), opt)
+    assert torch.isfinite(loss).all()
+    # oracle: same step in float64
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in sd.items()}
+    want, wlens = M.forward_ref(sd64, torch.from_numpy(x).double(), widths, hp, (u1, u2), training=True,
+                                bn_updates={}, use_nn_lstm=False)
+    wloss = M.ctc_sum_ref(want, labels, wlens, label_lens)
+    wloss.backward()
+    assert abs(loss[0].item() - wloss.item()) <= 2e-5 * abs(wloss.item())
+    for k, p in model.named_parameters():
+        if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
+            continue  # gradient is rounding noise on both sides; Adam turns noise into +-lr steps
+        g = sd64[k].grad
+        p1, _, _ = M.adam_clamp_ref(sd64[k].detach(), g, torch.zeros_like(g), torch.zeros_like(g), 1)
+        # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the gradient is not ~0
+        mask = g.abs() > 1e-6
+        assert (p.detach().double().cpu() - p1)[mask].abs().max().item() <= 2e-5

@@ -3,5 +3,7 @@ reference's own Python surface.  See DESIGN.md; the C ABI is include/vistaocr_b2
 from .alphabet import Alphabet  # noqa: F401
 from .decoder import ArgmaxDecoder  # noqa: F401
 from .warpctc import CTCLoss  # noqa: F401
+from .cnnlstm import CnnOcrModel  # noqa: F401
+from .optim import ClampAdam, train_step  # noqa: F401
 
-__all__ = ["Alphabet", "ArgmaxDecoder", "CTCLoss"]
+__all__ = ["Alphabet", "ArgmaxDecoder", "CTCLoss", "CnnOcrModel", "ClampAdam", "train_step"]

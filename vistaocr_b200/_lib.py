@@ -24,6 +24,25 @@ PROTOTYPES = {
     "vocr_greedy_decode_f32": (c_int, [c_p, c_int, c_int, c_int, c_p, c_f, c_p, c_p, c_p, c_p, c_int, c_p]),
     "vocr_ctc_workspace_size": (c_sz, [c_int, c_int, c_int, c_int]),
     "vocr_ctc_loss_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_sz, c_p]),
+    "vocr_gemm_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_int, c_p, c_int, c_p, c_int, c_p, c_int,
+                              c_int, c_p]),
+    "vocr_colsum_f32": (c_int, [c_p, c_ll, c_int, c_int, c_p, c_int, c_p]),
+    "vocr_conv_weight_layout_f32": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p]),
+    "vocr_conv3x3_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
+    "vocr_conv3x3_wgrad_workspace_size": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
+    "vocr_conv3x3_wgrad_f32": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
+    "vocr_rds_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
+    "vocr_rds_unpool_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
+    "vocr_bn_finalize_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_f, c_f, c_int, c_p, c_p, c_p, c_p, c_int, c_p]),
+    "vocr_bn_relu_apply_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_p]),
+    "vocr_bn_relu_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll,
+                                     c_ll, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "vocr_fracpool_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "vocr_fracpool_bwd_f32": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "vocr_bilstm_workspace_size": (c_sz, [c_int, c_int, c_int]),
+    "vocr_bilstm_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
+    "vocr_bilstm_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
+    "vocr_clamp_adam_f32": (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
 }
 
 _lib = None

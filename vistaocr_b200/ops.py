@@ -1,0 +1,341 @@
+"""Autograd-aware host wrappers over the C ABI (include/vistaocr_b200.h).
+
+Every op below launches hand-written CUDA kernels through ctypes on torch's current stream; torch itself only
+provides device memory, autograd bookkeeping and a few weight-layout views.  There is no fallback path: a missing
+library or a non-CUDA tensor raises.
+Layouts: CNN activations NHWC fp32 [B,H,W,C]; sequences time-major [T,B,F].
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+
+F32 = torch.float32
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _off(t, elems):
+    """Device pointer `elems` fp32 elements into t."""
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + 4 * elems)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense GEMM
+# ---------------------------------------------------------------------------------------------------------------
+def gemm(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
+         c_off=0):
+    st = lib().vocr_gemm_f32(int(transa), int(transb), M, N, K, _off(A, a_off), lda, _off(B, b_off), ldb,
+                             _off(C, c_off), ldc, ptr(bias), int(relu), int(accumulate), stream())
+    check(st, "vocr_gemm_f32")
+
+
+def colsum(x2d, rows, cols, ld, out, accumulate=False, x_off=0):
+    st = lib().vocr_colsum_f32(_off(x2d, x_off), rows, cols, ld, ptr(out), int(accumulate), stream())
+    check(st, "vocr_colsum_f32")
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b (optionally ReLU); x [M,K], W [N,K] (nn.Linear layout)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x, w = _c(x), _c(w)
+        _lib.require_cuda(x, "x", F32)
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty((M, N), dtype=F32, device=x.device)
+        gemm(0, 1, M, N, K, x, K, w, K, y, N, bias=b, relu=relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.relu:
+            dy = torch.where(y > 0, dy, torch.zeros((), dtype=F32, device=dy.device))
+        M, K = x.shape
+        N = w.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(0, 0, M, K, N, dy, N, w, K, dx, K)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            gemm(1, 0, N, K, M, dy, N, x, K, dw, K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty((N,), dtype=F32, device=x.device)
+            colsum(dy, M, N, N, db)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, relu=False):
+    return _Linear.apply(x, w, b, relu)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# conv3x3 + BatchNorm + ReLU block
+# ---------------------------------------------------------------------------------------------------------------
+def _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, stats):
+    z = torch.empty((B, H, W, Cout), dtype=F32, device=x.device)
+    st = lib().vocr_conv3x3_fwd_f32(ptr(x), ptr(wk), ptr(bias), ptr(z), B, H, W, Cin, Cout, ptr(stats), stream())
+    check(st, "vocr_conv3x3_fwd_f32")
+    return z
+
+
+def _weight_layout(w, want_k, want_d):
+    Cout, Cin = w.shape[0], w.shape[1]
+    wk = torch.empty((9 * Cin, Cout), dtype=F32, device=w.device) if want_k else None
+    wd = torch.empty((9 * Cout, Cin), dtype=F32, device=w.device) if want_d else None
+    st = lib().vocr_conv_weight_layout_f32(ptr(w), Cin, Cout, ptr(wk), ptr(wd), stream())
+    check(st, "vocr_conv_weight_layout_f32")
+    return wk, wd
+
+
+def _conv_wgrad(x, dz, B, H, W, Cin, Cout):
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=x.device)
+    wsb = lib().vocr_conv3x3_wgrad_workspace_size(B, H, W, Cin, Cout)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=x.device)
+    st = lib().vocr_conv3x3_wgrad_f32(ptr(x), ptr(dz), ptr(dw), B, H, W, Cin, Cout, ptr(ws), wsb, stream())
+    check(st, "vocr_conv3x3_wgrad_f32")
+    return dw
+
+
+class _ConvBNReLU(torch.autograd.Function):
+    """a = relu(batchnorm(conv3x3(x) + bias)).  x NHWC [B,H,W,Cin]; weight [Cout,Cin,3,3] (state_dict layout).
+    seq_layout=True writes a as the time-major sequence [W, B, H*Cout] (feature = y*Cout + c)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps, seq_layout):
+        x = _c(x)
+        _lib.require_cuda(x, "x", F32)
+        B, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        dev = x.device
+        wk, _ = _weight_layout(_c(weight), True, False)
+        stats = torch.zeros((2 * Cout,), dtype=torch.float64, device=dev) if training else None
+        z = _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, stats)
+        scale = torch.empty((Cout,), dtype=F32, device=dev)
+        shift = torch.empty((Cout,), dtype=F32, device=dev)
+        mean = torch.empty((Cout,), dtype=F32, device=dev)
+        invstd = torch.empty((Cout,), dtype=F32, device=dev)
+        st = lib().vocr_bn_finalize_f32(ptr(stats), B * H * W, ptr(gamma), ptr(beta), ptr(running_mean),
+                                        ptr(running_var), float(momentum), float(eps), int(training), ptr(scale),
+                                        ptr(shift), ptr(mean), ptr(invstd), Cout, stream())
+        check(st, "vocr_bn_finalize_f32")
+        if seq_layout:
+            a = torch.empty((W, B, H * Cout), dtype=F32, device=dev)
+            strides = (H * Cout, Cout, B * H * Cout)
+        else:
+            a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
+            strides = (H * W * Cout, W * Cout, Cout)
+        st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), ptr(a), B, H, W, Cout, strides[0],
+                                          strides[1], strides[2], stream())
+        check(st, "vocr_bn_relu_apply_f32")
+        ctx.save_for_backward(x, weight, z, scale, shift, mean, invstd)
+        ctx.dims = (B, H, W, Cin, Cout, strides, bool(training))
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, weight, z, scale, shift, mean, invstd = ctx.saved_tensors
+        B, H, W, Cin, Cout, strides, training = ctx.dims
+        dev = x.device
+        da = _c(da)
+        dz = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
+        dgamma = torch.empty((Cout,), dtype=F32, device=dev)
+        dbeta = torch.empty((Cout,), dtype=F32, device=dev)
+        dbias = torch.empty((Cout,), dtype=F32, device=dev)
+        red = torch.empty((3 * Cout,), dtype=torch.float64, device=dev)
+        st = lib().vocr_bn_relu_bwd_f32(ptr(da), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                                        int(training), B, H, W, Cout, strides[0], strides[1], strides[2], ptr(dz),
+                                        ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red), stream())
+        check(st, "vocr_bn_relu_bwd_f32")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = _weight_layout(_c(weight), False, True)
+            dx = _conv_fwd(dz, wd, None, B, H, W, Cout, Cin, None)
+        dw = _conv_wgrad(x, dz, B, H, W, Cin, Cout)
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
+
+
+def conv_bn_relu(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5,
+                 seq_layout=False):
+    return _ConvBNReLU.apply(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps,
+                             seq_layout)
+
+
+class _RapidDS(torch.autograd.Function):
+    """y = maxpool2x2(relu(conv3x3(x) + bias)), Cout = 16 (reference cnnlstm.py:114-121)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _c(x)
+        _lib.require_cuda(x, "x", F32)
+        B, H, W, Cin = x.shape
+        assert weight.shape[0] == 16
+        dev = x.device
+        wk, _ = _weight_layout(_c(weight), True, False)
+        y = torch.empty((B, H // 2, W // 2, 16), dtype=F32, device=dev)
+        need_bwd = any(ctx.needs_input_grad)
+        arg = torch.empty((B, H // 2, W // 2, 16), dtype=torch.uint8, device=dev) if need_bwd else None
+        st = lib().vocr_rds_fwd_f32(ptr(x), ptr(wk), ptr(bias), ptr(y), ptr(arg), B, H, W, Cin, stream())
+        check(st, "vocr_rds_fwd_f32")
+        ctx.save_for_backward(x, weight, y, arg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y, arg = ctx.saved_tensors
+        B, H, W, Cin = x.shape
+        dev = x.device
+        dy = _c(dy)
+        dpre = torch.empty((B, H, W, 16), dtype=F32, device=dev)
+        st = lib().vocr_rds_unpool_f32(ptr(dy), ptr(y), ptr(arg), ptr(dpre), B, H, W, stream())
+        check(st, "vocr_rds_unpool_f32")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = _weight_layout(_c(weight), False, True)
+            dx = _conv_fwd(dpre, wd, None, B, H, W, 16, Cin, None)
+        dw = _conv_wgrad(x, dpre, B, H, W, Cin, 16)
+        db = torch.empty((16,), dtype=F32, device=dev)
+        colsum(dpre, B * H * W, 16, 16, db)
+        return dx, dw, db
+
+
+def rapid_ds(x, weight, bias):
+    return _RapidDS.apply(x, weight, bias)
+
+
+class _FracPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, samples):
+        x = _c(x)
+        _lib.require_cuda(x, "x", F32)
+        B, H, W, C = x.shape
+        Ho, Wo = int(H * 0.5), int(W * 0.7)  # same float64 product + truncation as ATen / the reference
+        samples = _c(samples.to(device=x.device, dtype=F32))
+        assert samples.shape == (B, C, 2)
+        y = torch.empty((B, Ho, Wo, C), dtype=F32, device=x.device)
+        idx = torch.empty((B, Ho, Wo, C), dtype=torch.int32, device=x.device) if x.requires_grad else None
+        st = lib().vocr_fracpool_fwd_f32(ptr(x), ptr(samples), ptr(y), ptr(idx), B, H, W, C, Ho, Wo, stream())
+        check(st, "vocr_fracpool_fwd_f32")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, H, W, C, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        B, H, W, C, Ho, Wo = ctx.dims
+        dy = _c(dy)
+        dx = torch.empty((B, H, W, C), dtype=F32, device=dy.device)
+        st = lib().vocr_fracpool_bwd_f32(ptr(dy), ptr(idx), ptr(dx), B, H, W, C, Ho, Wo, stream())
+        check(st, "vocr_fracpool_bwd_f32")
+        return dx, None
+
+
+def fracpool(x, samples):
+    return _FracPool.apply(x, samples)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bidirectional LSTM layer
+# ---------------------------------------------------------------------------------------------------------------
+class _BiLSTMLayer(torch.autograd.Function):
+    """x [T,B,Din]; w_ih [8H,Din] (forward rows then reverse rows); w_hh [2,4H,H]; bias [8H] (= b_ih + b_hh);
+    lens_dev int32 [B] on the device; tmax = max(lens) (python int).  Returns out [T,B,2H]."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, bias, lens_dev, tmax, save):
+        x, w_ih, w_hh, bias = _c(x), _c(w_ih), _c(w_hh), _c(bias)
+        _lib.require_cuda(x, "x", F32)
+        T, B, Din = x.shape
+        H = w_hh.shape[2]
+        dev = x.device
+        xproj = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev)
+        gemm(0, 1, T * B, 8 * H, Din, x, Din, w_ih, Din, xproj, 8 * H, bias=bias)
+        out = torch.empty((T, B, 2 * H), dtype=F32, device=dev)
+        gates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev) if save else None
+        cst = torch.empty((T, B, 2, H), dtype=F32, device=dev) if save else None
+        wsb = lib().vocr_bilstm_workspace_size(B, H, 0)
+        if wsb == 0:
+            raise _lib.VocrError("vocr_bilstm: unsupported hidden size %d (max 512)" % H)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        st = lib().vocr_bilstm_fwd_f32(ptr(xproj), ptr(w_hh), ptr(lens_dev), ptr(out), ptr(gates), ptr(cst), T, B, H,
+                                       int(tmax), ptr(ws), wsb, stream())
+        check(st, "vocr_bilstm_fwd_f32")
+        if save:
+            ctx.save_for_backward(x, w_ih, w_hh, lens_dev, gates, cst, out)
+            ctx.tmax = int(tmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w_ih, w_hh, lens_dev, gates, cst, out = ctx.saved_tensors
+        T, B, Din = x.shape
+        H = w_hh.shape[2]
+        dev = x.device
+        dout = _c(dout)
+        dgates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev)
+        wsb = lib().vocr_bilstm_workspace_size(B, H, 1)
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+        st = lib().vocr_bilstm_bwd_f32(ptr(dout), ptr(w_hh), ptr(lens_dev), ptr(gates), ptr(cst), ptr(dgates), T, B,
+                                       H, ctx.tmax, ptr(ws), wsb, stream())
+        check(st, "vocr_bilstm_bwd_f32")
+        dx = dw_ih = dw_hh = db = None
+        M = T * B
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(0, 0, M, Din, 8 * H, dgates, 8 * H, w_ih, Din, dx, Din)
+        if ctx.needs_input_grad[1]:
+            dw_ih = torch.empty_like(w_ih)
+            gemm(1, 0, 8 * H, Din, M, dgates, 8 * H, x, Din, dw_ih, Din)
+        if ctx.needs_input_grad[2]:
+            # dW_hh[d] = sum_t dgates[t,:,d,:]^T h_prev[t,:,d,:]; h_prev is `out` shifted one step along the
+            # direction's time order (rows beyond a sample's length are zero in both operands)
+            dw_hh = torch.zeros_like(w_hh)
+            if T > 1:
+                K = (T - 1) * B
+                gemm(1, 0, 4 * H, H, K, dgates, 8 * H, out, 2 * H, dw_hh, H, a_off=B * 8 * H, b_off=0, c_off=0)
+                gemm(1, 0, 4 * H, H, K, dgates, 8 * H, out, 2 * H, dw_hh, H, a_off=4 * H, b_off=B * 2 * H + H,
+                     c_off=4 * H * H)
+        if ctx.needs_input_grad[3]:
+            db = torch.empty((8 * H,), dtype=F32, device=dev)
+            colsum(dgates, M, 8 * H, 8 * H, db)
+        return dx, dw_ih, dw_hh, db, None, None, None
+
+
+def bilstm_layer(x, w_ih, w_hh, bias, lens_dev, tmax, save=True):
+    return _BiLSTMLayer.apply(x, w_ih, w_hh, bias, lens_dev, tmax, save)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused clamp + Adam over flat buffers
+# ---------------------------------------------------------------------------------------------------------------
+def clamp_adam_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clamp=5.0,
+                    grad_scale=1.0):
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _lib.require_cuda(t, n, F32)
+    st = lib().vocr_clamp_adam_f32(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr), float(betas[0]),
+                                   float(betas[1]), float(eps), float(weight_decay), float(clamp), float(grad_scale),
+                                   stream())
+    check(st, "vocr_clamp_adam_f32")
+
+
+def out_hw(h, w, n_rds):
+    """Output (h, w) of rapid_ds + cnn for an input (h, w): reference cnn_input_size_to_output_size
+    (cnnlstm.py:211-260): MaxPool2d floors the half, FractionalMaxPool2d floors x*0.5 / x*0.7 in float64."""
+    for _ in range(n_rds):
+        h, w = math.floor((h - 2) / 2 + 1), math.floor((w - 2) / 2 + 1)
+    for _ in range(2):
+        h, w = math.floor(h * 0.5), math.floor(w * 0.7)
+    return h, w
