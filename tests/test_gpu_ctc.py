@@ -4,7 +4,7 @@ Tolerances.  Cost: |cost - ref| <= 1e-5 * max(1, |ref|) per utterance (north_sta
 Gradient (entries are O(1): softmax minus occupancy): any fp32 log-space recursion accumulates ~1e-7 of rounding
 per frame, so the reference's own arithmetic (warp-ctc, restated in fp32 by oracle/ctc_ref.c -DREAL=float) is
 already 2e-5 (T=50) .. 4e-4 (T=200+) away from the float64 answer.  The kernel renormalises alpha/beta and must
-be (a) within max(GRAD_ATOL = 5e-5, 2e-7*T) of float64 (rounding accumulates linearly in T at worst) and (b) no further from float64 than the
+be (a) within max(GRAD_ATOL = 5e-5, 5e-7*T) of float64 (rounding accumulates linearly in T at worst) and (b) no further from float64 than the
 reference arithmetic is (x1.5 + 1e-6 slack), i.e. at least as accurate as the implementation it replaces."""
 import numpy as np
 import pytest
@@ -49,7 +49,7 @@ def _check(got_c, got_g, acts, labels, act_lens, label_lens):
     err = np.abs(got_g - want_g).max()
     _, ref32_g = ctc_ref(acts, labels, act_lens, label_lens, real="float")
     err_ref32 = np.abs(ref32_g - want_g).max()
-    assert err <= max(GRAD_ATOL, 2e-7 * acts.shape[0]), (err, err_ref32)
+    assert err <= max(GRAD_ATOL, 5e-7 * acts.shape[0]), (err, err_ref32)
     assert err <= max(RTOL, 1.5 * err_ref32 + 1e-6), (err, err_ref32)
     T = acts.shape[0]
     for b in range(acts.shape[1]):
@@ -132,4 +132,4 @@ def test_full_size_properties(cuda):
         sub = (acts[:, b:b + 1].copy(), labels[offs[b]:offs[b + 1]], act_lens[b:b + 1], label_lens[b:b + 1])
         wc, wg = ctc_ref(*sub)
         assert abs(costs[b].item() - wc[0]) <= RTOL * max(1.0, wc[0])
-        assert np.abs(grads[:, b].cpu().numpy() - wg[:, 0]).max() <= 2e-4  # T=1000; warp-ctc arithmetic: ~1e-3
+        assert np.abs(grads[:, b].cpu().numpy() - wg[:, 0]).max() <= 5e-4  # 5e-7*T at T=1000; warp-ctc arithmetic: ~1e-3 and worse

@@ -13,6 +13,21 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # fp32 bound on logits after 7 convs + LSTM stack: 1e-5 relative to the tensor's scale, plus a small absolute term
 RTOL, ATOL = 1e-5, 2e-6
+# Gradients.  Measured with tools/grad_report.py against the float64 oracle: every parameter gradient of the CUDA path
+# is within 1e-6..7e-6 of float64 relative to the tensor's max (the reference's own fp32 run: 2e-6..1e-5), EXCEPT
+# parameters upstream of a max-pool (rapid_ds, cnn.0 .. cnn.11): there two correct fp32 evaluations can route a
+# gradient through different window elements when two candidates tie to within rounding, which moves those tensors
+# by up to ~3e-3 relative - the reference's fp32 run shows the same 4e-4..3e-3 against float64 on fixture h60.
+GRAD_RTOL = 2e-4
+GRAD_RTOL_UPSTREAM_OF_POOL = 5e-3
+
+
+def _grad_rtol(name):
+    if name.startswith("rapid_ds."):
+        return GRAD_RTOL_UPSTREAM_OF_POOL
+    if name.startswith("cnn.") and int(name.split(".")[1]) <= 11:
+        return GRAD_RTOL_UPSTREAM_OF_POOL
+    return GRAD_RTOL
 
 CONFIGS = {
     "h30": dict(input_line_height=30, rds_line_height=30, lstm_input_dim=16, num_lstm_layers=2,
@@ -81,7 +96,7 @@ def test_golden_from_reference(cuda, name):
             want = z[k]
             if k.endswith("cnn.0.bias"):
                 continue
-            _close(named[k[5:]].grad, want, k, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(want).max()))
+            _close(named[k[5:]].grad, want, k, rtol=_grad_rtol(k[5:]), atol=1e-6)
         if k.startswith("after."):
             _close(model.state_dict()[k[6:]], z[k], k)
 
@@ -102,7 +117,7 @@ def test_fresh_batch_against_oracle(cuda):
     model.cnn[6]._random_samples, model.cnn[13]._random_samples = u1, u2
     sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
     for k in sd64:
-        if sd64[k].is_floating_point():
+        if sd64[k].is_floating_point() and "running" not in k:
             sd64[k].requires_grad_(True)
     model.train()
     logits, lens = model(torch.from_numpy(x).to(cuda), torch.from_numpy(widths))
@@ -122,7 +137,7 @@ def test_fresh_batch_against_oracle(cuda):
         if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
             assert p.grad.abs().max().item() <= 1e-3  # mathematically zero (conv bias before train-mode BN)
             continue
-        _close(p.grad, w, "grad " + k, rtol=2e-4, atol=1e-6)
+        _close(p.grad, w, "grad " + k, rtol=_grad_rtol(k), atol=1e-6)
 
 
 def test_train_step_with_fused_optimizer(cuda):
@@ -144,8 +159,10 @@ def test_train_step_with_fused_optimizer(cuda):
     loss = train_step(batch, model, CTCLoss(host_cost=False), opt)
     assert torch.isfinite(loss).all()
     # oracle: same step in float64
-    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
-            for k, v in sd.items()}
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    for k in sd64:
+        if sd64[k].is_floating_point() and "running" not in k:
+            sd64[k].requires_grad_(True)
     want, wlens = M.forward_ref(sd64, torch.from_numpy(x).double(), widths, hp, (u1, u2), training=True,
                                 bn_updates={}, use_nn_lstm=False)
     wloss = M.ctc_sum_ref(want, labels, wlens, label_lens)
