@@ -47,6 +47,80 @@ PROTOTYPES = {
 
 _lib = None
 
+# kernels launched per entry-point call (for bench.py's gpu_launches claim) and algorithmic work per call
+# (flops for the GEMM-shaped kernels, bytes for the HBM-bound ones) as a function of the ctypes argument tuple
+KERNELS_PER_CALL = {
+    "vocr_greedy_decode_f32": 2, "vocr_ctc_loss_f32": 4, "vocr_gemm_f32": 1, "vocr_colsum_f32": 1,
+    "vocr_conv_weight_layout_f32": 1, "vocr_conv3x3_fwd_f32": 1, "vocr_conv3x3_wgrad_f32": 2, "vocr_rds_fwd_f32": 1,
+    "vocr_rds_unpool_f32": 1, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
+    "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 1, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
+    "vocr_clamp_adam_f32": 1,
+}
+WORK = {
+    "vocr_gemm_f32": lambda a: ("flop", 2.0 * a[2] * a[3] * a[4]),
+    "vocr_conv3x3_fwd_f32": lambda a: ("flop", 2.0 * a[4] * a[5] * a[6] * 9 * a[7] * a[8]),
+    "vocr_conv3x3_wgrad_f32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5] * 9 * a[6] * a[7]),
+    "vocr_bilstm_fwd_f32": lambda a: ("flop", 2.0 * a[9] * a[7] * 8 * a[8] * a[8]),
+    "vocr_bilstm_bwd_f32": lambda a: ("flop", 2.0 * a[9] * a[7] * 8 * a[8] * a[8]),
+    "vocr_greedy_decode_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3]),
+    "vocr_ctc_loss_f32": lambda a: ("byte", 8.0 * a[5] * a[6] * a[7]),
+    "vocr_clamp_adam_f32": lambda a: ("byte", 28.0 * a[4]),
+}
+
+
+class Profiler:
+    """Counts entry-point calls / kernel launches and, when `timing` is on, brackets every call with CUDA events on
+    the launching stream (bench.py reads per-entry-point device time and work from here)."""
+
+    def __init__(self):
+        self.reset()
+        self.timing = False
+
+    def reset(self):
+        self.calls = {}
+        self.launches = 0
+        self.records = []  # (name, start_event, end_event, kind, work)
+
+    def summary(self):
+        out = {}
+        for name, s, e, kind, work in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "kind": kind, "work": 0.0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            d["work"] += work
+        return out
+
+
+PROFILER = Profiler()
+
+
+def _wrap(name, fn):
+    k = KERNELS_PER_CALL.get(name)
+    if k is None:
+        return fn
+    work_fn = WORK.get(name)
+
+    def call(*args):
+        p = PROFILER
+        p.calls[name] = p.calls.get(name, 0) + 1
+        p.launches += k
+        if not p.timing:
+            return fn(*args)
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        st = fn(*args)
+        e.record()
+        kind, work = work_fn(args) if work_fn else ("none", 0.0)
+        p.records.append((name, s, e, kind, work))
+        return st
+
+    return call
+
+
+class _Lib:
+    pass
+
 
 class VocrError(RuntimeError):
     pass
@@ -60,11 +134,13 @@ def lib():
                 "vistaocr_b200: %s is missing - build it with `python -m vistaocr_b200.build` "
                 "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
         l = ctypes.CDLL(LIB_PATH)
+        w = _Lib()
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = l
+            setattr(w, name, _wrap(name, fn))
+        _lib = w
     return _lib
 
 
