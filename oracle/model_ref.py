@@ -132,9 +132,9 @@ def bilstm_ref(sd, x, lens, num_layers, dropout_masks=None):
 def bilstm_nn(sd, x, lens, num_layers, hidden, dtype):
     """Same computation through torch.nn.LSTM on a packed sequence - literally what the reference runs."""
     lstm = torch.nn.LSTM(x.shape[2], hidden, num_layers=num_layers, bidirectional=True).to(dtype)
-    lstm.load_state_dict({k[len("lstm."):]: v for k, v in sd.items() if k.startswith("lstm.")})
+    weights = {k[len("lstm."):]: v for k, v in sd.items() if k.startswith("lstm.")}
     packed = torch.nn.utils.rnn.pack_padded_sequence(x, list(lens))
-    out, _ = lstm(packed)
+    out, _ = torch.func.functional_call(lstm, weights, (packed,))  # keeps autograd attached to `sd`'s tensors
     out, _ = torch.nn.utils.rnn.pad_packed_sequence(out)
     return out
 

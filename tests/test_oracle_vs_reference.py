@@ -1,0 +1,99 @@
+"""CPU, authoring container only: the oracle restatements against the UNMODIFIED reference imported read-only from
+/root/reference/src (skipped on the GPU box, where the reference does not exist; the committed fixtures in
+tests/golden/ carry the same comparison there)."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference/src"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle.decode_ref import uxxxx_to_utf8
+    stub = types.ModuleType("textutils")  # the real one needs ICU + absolute data paths (textutils.py:3,9-35)
+    stub.uxxxx_to_utf8 = uxxxx_to_utf8
+    saved = {k: sys.modules.get(k) for k in ("textutils", "alphabet", "decoder", "models", "models.cnnlstm")}
+    sys.modules["textutils"] = stub
+    for k in ("alphabet", "decoder", "models", "models.cnnlstm"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, REF)
+    import alphabet
+    import decoder
+    from models import cnnlstm
+    yield types.SimpleNamespace(Alphabet=alphabet.Alphabet, ArgmaxDecoder=decoder.ArgmaxDecoder,
+                                CnnOcrModel=cnnlstm.CnnOcrModel)
+    sys.path.remove(REF)
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+
+
+def test_decode_oracle_equals_reference_decoder(ref):
+    from oracle.decode_ref import decode_loop
+    from tests.test_oracle_decode import _adversarial_logits
+    for A in (3, 80, 97, 121, 200):
+        rng = np.random.default_rng(A)
+        x = _adversarial_logits(rng, 29, 4, A)
+        lens = np.array([29, 20, 3, 0], np.int32)
+        alpha = ref.Alphabet(["<ctc-blank>"] + ["u%04x" % (0x61 + i) for i in range(A - 1)])
+        want = ref.ArgmaxDecoder(alpha).decode(torch.from_numpy(x), torch.from_numpy(lens), uxxxx=True)
+        assert decode_loop(x, lens, alpha.idx_to_char, uxxxx=True) == want
+
+
+def test_model_oracle_equals_reference_model(ref):
+    from oracle import model_ref as M
+    hp = dict(input_line_height=60, rds_line_height=30, lstm_input_dim=16, num_lstm_layers=2,
+              num_lstm_hidden_units=24, p_lstm_dropout=0.0)
+    A = 13
+    alpha = ref.Alphabet(["<ctc-blank>"] + ["u%04x" % (0x61 + i) for i in range(A - 1)])
+    model = ref.CnnOcrModel(alphabet=alpha, gpu=False, multigpu=False, verbose=False, **hp)
+    sd = M.make_state_dict(hp, A, seed=1)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    rng = np.random.default_rng(0)
+    x, widths, _, _ = M.synth_batch(rng, 3, 60, 60, 140, A, n_rds=1)
+    u1 = torch.from_numpy(rng.random((3, 64, 2)).astype(np.float32))
+    u2 = torch.from_numpy(rng.random((3, 128, 2)).astype(np.float32))
+    model.cnn[6]._random_samples, model.cnn[13]._random_samples = u1, u2
+    for training in (False, True):
+        model.train(training)
+        with torch.no_grad():
+            want, lens = model(torch.from_numpy(x), torch.from_numpy(widths))
+        got, glens = M.forward_ref(sd, torch.from_numpy(x), widths, hp, (u1, u2), training=training,
+                                   bn_updates={} if training else None)
+        assert glens.tolist() == lens.tolist()
+        assert (got - want).abs().max().item() <= 1e-6
+        got2, _ = M.forward_ref(sd, torch.from_numpy(x), widths, hp, (u1, u2), training=training,
+                                bn_updates={} if training else None, use_nn_lstm=False)
+        assert (got2 - want).abs().max().item() <= 2e-6
+
+
+def test_our_model_class_mirrors_reference_state_dict_and_init(ref):
+    from vistaocr_b200 import CnnOcrModel
+    for hp in (dict(input_line_height=30, rds_line_height=30), dict(input_line_height=120, rds_line_height=30)):
+        hp.update(lstm_input_dim=8, num_lstm_layers=2, num_lstm_hidden_units=12, p_lstm_dropout=0.5)
+        alpha = ref.Alphabet(list(range(17)))
+        torch.manual_seed(7)
+        r = ref.CnnOcrModel(alphabet=alpha, gpu=False, multigpu=False, verbose=False, **hp)
+        torch.manual_seed(7)
+        m = CnnOcrModel(alphabet=alpha, gpu=False, multigpu=False, verbose=False, **hp)
+        a, b = r.state_dict(), m.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+        assert [n for n, _ in r.named_parameters()] == [n for n, _ in m.named_parameters()]
+        for w in (15, 200, 350, 801):
+            assert m.cnn_input_size_to_output_size((hp["input_line_height"], w)) == \
+                r.cnn_input_size_to_output_size((hp["input_line_height"], w))
+        with pytest.raises(Exception):
+            CnnOcrModel(30)
+        with pytest.raises(Exception):
+            CnnOcrModel(alphabet=alpha, **dict(hp, input_line_height=45, rds_line_height=30))

@@ -14,6 +14,93 @@ import torch.distributed as dist
 from . import ops
 
 
+class FlatGradReducer:
+    """One flat fp32 gradient buffer for a list of parameters (each `p.grad` is a view into it) plus the data-parallel
+    exchange: contiguous buckets of the buffer are all-reduced (SUM) asynchronously as soon as autograd has produced
+    every gradient of the bucket, last parameters first (prob layer, top LSTM layer ... CNN), so the collective
+    overlaps the remaining backward.  Device-agnostic (NCCL on GPUs; the gloo tests drive it on CPU)."""
+
+    def __init__(self, params, process_group=None, bucket_elems=4 << 20, overlap=True):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]  # keep every view 16-B aligned
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        self.flat_g = torch.zeros(self.offsets[-1], dtype=torch.float32, device=dev)
+        self.gviews = []
+        for p, o in zip(self.params, self.offsets):
+            gv = self.flat_g[o:o + p.numel()].view_as(p)
+            p.grad = gv
+            self.gviews.append(gv)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.handles = []
+        self.buckets = []  # (lo, hi, n_params) element ranges of flat_g, in the order backward completes them
+        self.collectives = 0
+        if self.world > 1:
+            self._make_buckets(bucket_elems)
+            if overlap:
+                for i, p in enumerate(self.params):
+                    p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_buckets(self, bucket_elems):
+        self.bucket_of = [0] * len(self.params)
+        hi = len(self.params)
+        while hi > 0:
+            lo = hi - 1
+            while lo > 0 and self.offsets[hi] - self.offsets[lo] < bucket_elems:
+                lo -= 1
+            for i in range(lo, hi):
+                self.bucket_of[i] = len(self.buckets)
+            self.buckets.append((self.offsets[lo], self.offsets[hi], hi - lo))
+            hi = lo
+        self._reset()
+
+    def _reset(self):
+        self.pending = [cnt for (_, _, cnt) in self.buckets]
+        self.launched = set()
+
+    def _launch(self, b):
+        lo, hi, _ = self.buckets[b]
+        self.handles.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        self.launched.add(b)
+        self.collectives += 1
+
+    def _make_hook(self, i):
+        def hook(p):
+            if p.grad is not self.gviews[i]:  # someone replaced .grad (zero_grad(set_to_none=True)): fold it back
+                self.gviews[i].copy_(p.grad)
+                p.grad = self.gviews[i]
+            b = self.bucket_of[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def zero(self):
+        self.flat_g.zero_()
+        for p, gv in zip(self.params, self.gviews):
+            p.grad = gv
+
+    def finish(self):
+        """Fold stray .grad tensors back into the flat buffer, launch whatever has not been launched, wait."""
+        for p, gv in zip(self.params, self.gviews):
+            if p.grad is None:
+                gv.zero_()
+            elif p.grad is not gv:
+                gv.copy_(p.grad)
+            p.grad = gv
+        if self.world > 1:
+            for b in range(len(self.buckets)):
+                if b not in self.launched:
+                    self._launch(b)
+            for h in self.handles:
+                h.wait()
+            self.handles = []
+            self._reset()
+
+
 class ClampAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clamp=5.0,
                  process_group=None, bucket_elems=4 << 20, overlap=True):
@@ -21,107 +108,36 @@ class ClampAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise ValueError("ClampAdam keeps all parameters in one flat buffer: pass a single parameter group")
-        self._params = [p for p in self.param_groups[0]["params"] if p.requires_grad]
-        dev = self._params[0].device
-        if dev.type != "cuda":
+        plist = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        if plist[0].device.type != "cuda":
             raise ops._lib.VocrError("ClampAdam needs CUDA parameters: there is no CPU path")
-        sizes = [(p.numel() + 3) // 4 * 4 for p in self._params]  # keep every view 16-B aligned
-        self._offsets = [0]
-        for s in sizes:
-            self._offsets.append(self._offsets[-1] + s)
-        n = self._offsets[-1]
+        self.reducer = FlatGradReducer(plist, process_group, bucket_elems, overlap)
+        n = self.reducer.offsets[-1]
+        dev = plist[0].device
         self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
-        self._gviews = []
         with torch.no_grad():
-            for p, o in zip(self._params, self._offsets):
+            for p, o in zip(plist, self.reducer.offsets):
                 view = self.flat_p[o:o + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view
-                gv = self.flat_g[o:o + p.numel()].view_as(p)
-                p.grad = gv
-                self._gviews.append(gv)
         self._step = 0
-        # ---- data parallel plumbing ----
-        self._pg = process_group
-        self._world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self._handles = []
-        self._buckets = []   # (lo, hi) element ranges of flat_g, in the order backward completes them
-        self._pending = {}
-        if self._world > 1:
-            self._make_buckets(bucket_elems)
-            if overlap:
-                for i, p in enumerate(self._params):
-                    p.register_post_accumulate_grad_hook(self._make_hook(i))
-            self._overlap = overlap
 
-    # buckets are contiguous ranges of the flat buffer taken from the END (backward reaches the last parameters -
-    # prob layer, top LSTM layer - first)
-    def _make_buckets(self, bucket_elems):
-        self._bucket_of = [0] * len(self._params)
-        hi = len(self._params)
-        bidx = 0
-        while hi > 0:
-            lo = hi
-            while lo > 0 and self._offsets[hi] - self._offsets[lo] < bucket_elems:
-                lo -= 1
-            self._buckets.append((self._offsets[lo], self._offsets[hi], hi - lo))
-            for i in range(lo, hi):
-                self._bucket_of[i] = bidx
-            bidx += 1
-            hi = lo
-        self._reset_pending()
-
-    def _reset_pending(self):
-        self._pending = {b: cnt for b, (_, _, cnt) in enumerate(self._buckets)}
-        self._launched = set()
-
-    def _launch_bucket(self, b):
-        lo, hi, _ = self._buckets[b]
-        self._handles.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self._pg, async_op=True))
-        self._launched.add(b)
-
-    def _make_hook(self, i):
-        def hook(p):
-            if p.grad is not self._gviews[i]:  # someone replaced .grad (zero_grad(set_to_none=True)): fold it back
-                self._gviews[i].copy_(p.grad)
-                p.grad = self._gviews[i]
-            b = self._bucket_of[i]
-            self._pending[b] -= 1
-            if self._pending[b] == 0:
-                self._launch_bucket(b)
-        return hook
+    @property
+    def flat_g(self):
+        return self.reducer.flat_g
 
     def zero_grad(self, set_to_none=False):
-        self.flat_g.zero_()
-        for p, gv in zip(self._params, self._gviews):
-            p.grad = gv
+        self.reducer.zero()
 
     @torch.no_grad()
     def step(self, closure=None):
-        for p, gv in zip(self._params, self._gviews):
-            if p.grad is None:
-                gv.zero_()
-            elif p.grad is not gv:
-                gv.copy_(p.grad)
-            p.grad = gv
-        if self._world > 1:
-            for b in range(len(self._buckets)):
-                if b not in self._launched:
-                    self._launch_bucket(b)
-            for h in self._handles:
-                h.wait()
-            self._handles = []
-            self._reset_pending()
+        self.reducer.finish()
         g = self.param_groups[0]
         self._step += 1
-        ops.clamp_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._step, lr=g["lr"],
+        ops.clamp_adam_step(self.flat_p, self.reducer.flat_g, self.flat_m, self.flat_v, self._step, lr=g["lr"],
                             betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], clamp=g["clamp"])
-
-    def gpu_launches_per_step(self):
-        return 1
 
 
 def broadcast_parameters(model, src=0, process_group=None):
