@@ -158,6 +158,19 @@ int vocr_clamp_adam_f32(float* p, const float* g, float* m, float* v, long long 
                         float beta2, float eps, float weight_decay, float clamp, float grad_scale,
                         vocr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (TMA + tcgen05.mma kind::tf32 + TMEM), error-compensated 3xTF32: fp32-level accuracy at tensor-core
+ * speed.  Same role as vocr_gemm_f32 (src/models/cnnlstm.py:143-154 -> cuBLAS).  Operands arrive pre-split by
+ * vocr_split_tf32_f32 (hi = rna_tf32(x), lo = x - hi; both planes keep x's layout):
+ *   a_mn = 0: A planes [M,K] row-major (lda)      a_mn = 1: A planes stored [K,M] (lda)
+ *   b_mn = 0: B planes [N,K] row-major (ldb)      b_mn = 1: B planes stored [K,N] (ldb)
+ * lda, ldb multiples of 4; plane bases 16-B aligned.  C[M,N] (ldc) = op(A) op(B) (+bias[n]) (+C) (ReLU).
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_split_tf32_f32(const float* x, float* hi, float* lo, long long n, vocr_stream_t stream);
+int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_hi, const float* a_lo, int lda,
+                        const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, const float* bias, int relu,
+                        int accumulate, vocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,50 @@
+"""GPU parity of the tcgen05 3xTF32 GEMM (csrc/tc_gemm.cu) against float64, all four operand-major combinations.
+Bound: max|C - ref| <= 1e-5 * max|ref| (the fp32 contract); also reported against the FFMA engine."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, a_mn, b_mn):
+    a = A.double().t() if a_mn else A.double()      # -> [M,K]
+    b = B.double() if b_mn else B.double().t()      # -> [K,N]
+    return a @ b
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (300, 200, 72), (1000, 512, 1024), (64, 96, 2304),
+                                   (257, 129, 36)])
+def test_tc_gemm_matches_float64(cuda, a_mn, b_mn, M, N, K):
+    from vistaocr_b200 import ops
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K + a_mn * 11 + b_mn * 13)
+    rup = lambda v: (v + 3) // 4 * 4
+    lda = rup(M) if a_mn else rup(K)
+    ldb = rup(N) if b_mn else rup(K)
+    A = torch.randn((K, lda) if a_mn else (M, lda), generator=g)
+    B = torch.randn((K, ldb) if b_mn else (N, ldb), generator=g)
+    Av = A[:, :M] if a_mn else A[:, :K]
+    Bv = B[:, :N] if b_mn else B[:, :K]
+    want = _ref(Av, Bv, a_mn, b_mn)
+    bias = torch.randn(N, generator=g)
+    C = torch.full((M, N + 1), 3.0, device=cuda)
+    As, Bs = ops.split_tf32(A.to(cuda)), ops.split_tf32(B.to(cuda))
+    ops.tc_gemm(a_mn, b_mn, M, N, K, As, lda, Bs, ldb, C, N + 1, bias=bias.to(cuda))
+    torch.cuda.synchronize()
+    got = C[:, :N].double().cpu()
+    err = (got - (want + bias.double())).abs().max().item()
+    assert err <= 1e-5 * want.abs().max().item(), (err, want.abs().max().item())
+    assert (C[:, N] == 3.0).all()
+    # accumulate + relu
+    C2 = torch.ones((M, N), device=cuda)
+    ops.tc_gemm(a_mn, b_mn, M, N, K, As, lda, Bs, ldb, C2, N, relu=True, accumulate=True)
+    err2 = (C2.double().cpu() - (want + 1).relu()).abs().max().item()
+    assert err2 <= 1e-5 * want.abs().max().item()
+
+
+def test_split_is_exact(cuda):
+    from vistaocr_b200 import ops
+    x = torch.randn(100003, device=cuda) * 100
+    hi, lo = ops.split_tf32(x)
+    assert torch.equal(hi + lo, x)
+    assert (hi.view(torch.int32) & 0x1fff).abs().max().item() == 0  # hi is exactly representable in TF32

@@ -1,0 +1,339 @@
+// Tensor-core GEMM for sm_100a: TMA-fed tcgen05.mma (kind::tf32) with the accumulator in TMEM, error-compensated
+// "3xTF32" so the result keeps fp32-level accuracy (north_star: 1e-5 relative in fp32):
+//     C = A_hi B_hi + A_lo B_hi + A_hi B_lo,     x_hi = rna_tf32(x),  x_lo = x - x_hi   (split done by the producer)
+// Replaces the FFMA engine (gemm_core.cuh) for the dense GEMMs of the path (LSTM input projections, bridge / prob
+// layers and their backward GEMMs; reference cnnlstm.py:143-154 -> cuBLAS).
+//
+// One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
+//   warp 0   TMA producer  : 4 operand tiles (A_hi, A_lo, B_hi, B_lo; 128 x 32 fp32 = 16 KB each, SWIZZLE_128B) per
+//                            k-block into a 3-stage shared-memory ring, mbarrier expect_tx / complete_tx
+//   warp 1   MMA issuer    : allocates 128 TMEM columns, one elected lane issues 12 tcgen05.mma per k-block
+//                            (4 k-steps of 8 x 3 products), tcgen05.commit releases the stage / signals the epilogue
+//   warps 2-5 epilogue     : tcgen05.ld (32 lanes x 32 columns per warp and pass) -> bias / ReLU / accumulate -> global
+// Both operand layouts are supported without any transpose pass: K-major (the reduction dimension is contiguous in
+// memory: activations [M,K], nn.Linear weights [N,K]) and MN-major (the reduction dimension is the row index: dY^T X
+// weight gradients, dY W data gradients); they differ only in the TMA box shape and the UMMA descriptor strides.
+// Every mbarrier wait is bounded and traps, so a descriptor bug surfaces as a launch error, not a hung GPU.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace vocr {
+
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;  // BK fp32 = 128 bytes = one swizzle row
+constexpr int kTcStages = 3;
+constexpr int kTcThreads = 192;
+constexpr int kTcTileBytes = kTcBM * kTcBK * 4;         // 16 KB
+constexpr int kTcStageBytes = 4 * kTcTileBytes;         // A_hi, A_lo, B_hi, B_lo
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 128;
+
+struct TcGemmParams {
+  float* c;
+  const float* bias;
+  int M, N, K, ldc;
+  int relu, accumulate;
+  int a_mn, b_mn;  // 1 = MN-major operand
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// UMMA shared-memory descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp): start address >> 4 in bits [0,14),
+// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type
+// SWIZZLE_128B = 2 in [61,64).  K-major SW128 tile: rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1).
+// MN-major SW128 tile: atoms of (32 elements of M/N) x (8 k rows) = 1024 B; SBO = stride between k groups, LBO = stride
+// between M/N groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                      TcGemmParams p) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
+                                                         ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + kTcStages;        // [stages]
+  uint64_t* tmem_full_bar = bars + 2 * kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+  const int num_kb = (p.K + kTcBK - 1) / kTcBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
+        mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
+        unsigned char* st = smem + (size_t)s * kTcStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
+        const int k0 = kb * kTcBK;
+        if (!p.a_mn) {
+          tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
+          tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
+        } else {
+          for (int j = 0; j < 4; ++j) {                                        // 4 boxes {32 m, 32 k rows}
+            tma_load_2d(st + j * 4096, &map_a_hi, &full_bar[s], m0 + 32 * j, k0);
+            tma_load_2d(st + kTcTileBytes + j * 4096, &map_a_lo, &full_bar[s], m0 + 32 * j, k0);
+          }
+        }
+        if (!p.b_mn) {
+          tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
+          tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+        } else {
+          for (int j = 0; j < 4; ++j) {
+            tma_load_2d(st + 2 * kTcTileBytes + j * 4096, &map_b_hi, &full_bar[s], n0 + 32 * j, k0);
+            tma_load_2d(st + 3 * kTcTileBytes + j * 4096, &map_b_lo, &full_bar[s], n0 + 32 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // instruction descriptor: D = F32 (1 << 4), A/B = TF32 (2 << 7, 2 << 10), majors, N >> 3 at bit 17, M >> 4 at 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      // per k-step (8 elements of K): K-major advances 32 B inside the swizzle row, MN-major advances one 1024-B atom
+      const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+      uint32_t accum = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
+        mbar_wait_or_trap(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < kTcBK / 8; ++ks) {
+          const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, 1024u);
+          const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, 1024u);
+          const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, 1024u);
+          const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, 1024u);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, accum);  // small terms first
+          accum = 1;
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    mbar_wait_or_trap(tmem_full_bar, 0);
+    tc_fence_after();
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+    const int m = m0 + lane_grp * 32 + lane;
+    float* crow = p.c + (size_t)m * p.ldc;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+#pragma unroll 1
+    for (int cb = 0; cb < kTcBN; cb += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cb;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + cb + j;
+          if (n >= p.N) break;
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float x = __uint_as_float(r[j + q]);
+            if (n + q < p.N) {
+              if (p.bias) x += __ldg(p.bias + n + q);
+              if (p.accumulate) x += crow[n + q];
+              if (p.relu) x = fmaxf(x, 0.f);
+            }
+            v[q] = x;
+          }
+          if (vec && n + 3 < p.N) {
+            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + q < p.N) crow[n + q] = v[q];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// x -> hi = round-to-nearest TF32 (exactly representable, so the tensor core reads it unchanged), lo = x - hi
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4,
+                  long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 h, l;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x[i]));
+    hi[i] = __uint_as_float(t);
+    lo[i] = x[i] - __uint_as_float(t);
+  }
+}
+
+}  // namespace vocr
+
+using namespace vocr;
+
+// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ---------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][cols] with leading dimension ld (elements); box = {box_cols, box_rows}; 128-B swizzle.
+static bool make_map_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
+                        int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+extern "C" int vocr_split_tf32_f32(const float* x, float* hi, float* lo, long long n, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(n >= 0);
+  if (n == 0) return VOCR_OK;
+  VOCR_REQUIRE(x && hi && lo);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
+  const long long n4 = al ? n / 4 : 0;
+  const int grid = (int)min((long long)kNumSMs * 8, ceil_div64(max(1ll, n / 4), 256));
+  split_tf32_kernel<<<grid, 256, 0, stream>>>(x, hi, lo, n4, n);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// C[M,N] = op(A) op(B) (+bias) (+C) (relu), operands pre-split into (hi, lo) planes with identical layout.
+//   a_mn = 0: A planes are [M,K] row-major (lda)      a_mn = 1: A planes are [K,M] row-major (lda)
+//   b_mn = 0: B planes are [N,K] row-major (ldb)      b_mn = 1: B planes are [K,N] row-major (ldb)
+// lda, ldb multiples of 4, plane bases 16-B aligned.
+extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_hi, const float* a_lo,
+                                   int lda, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc,
+                                   const float* bias, int relu, int accumulate, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(M >= 0 && N >= 0 && K >= 1);
+  if (M == 0 || N == 0) return VOCR_OK;
+  VOCR_REQUIRE(a_hi && a_lo && b_hi && b_lo && C);
+  VOCR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0);
+  VOCR_REQUIRE(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
+                 reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15) == 0);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  bool ok = true;
+  if (!a_mn) {
+    ok = ok && make_map_2d(&ma_hi, a_hi, M, K, lda, kTcBK, kTcBM) && make_map_2d(&ma_lo, a_lo, M, K, lda, kTcBK, kTcBM);
+  } else {
+    ok = ok && make_map_2d(&ma_hi, a_hi, K, M, lda, 32, kTcBK) && make_map_2d(&ma_lo, a_lo, K, M, lda, 32, kTcBK);
+  }
+  if (!b_mn) {
+    ok = ok && make_map_2d(&mb_hi, b_hi, N, K, ldb, kTcBK, kTcBN) && make_map_2d(&mb_lo, b_lo, N, K, ldb, kTcBK, kTcBN);
+  } else {
+    ok = ok && make_map_2d(&mb_hi, b_hi, K, N, ldb, 32, kTcBK) && make_map_2d(&mb_lo, b_lo, K, N, ldb, 32, kTcBK);
+  }
+  if (!ok) return VOCR_EXECUTION_FAILED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) !=
+        cudaSuccess)
+      return VOCR_EXECUTION_FAILED;
+    attr_set = true;
+  }
+  TcGemmParams p{C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0, b_mn ? 1 : 0};
+  dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM));
+  tc_gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}

@@ -40,6 +40,25 @@ def colsum(x2d, rows, cols, ld, out, accumulate=False, x_off=0):
     check(st, "vocr_colsum_f32")
 
 
+def split_tf32(t):
+    """(hi, lo) planes of a contiguous fp32 tensor for the 3xTF32 tensor-core GEMM: hi = rna_tf32(t), lo = t - hi."""
+    t = _c(t)
+    hi = torch.empty_like(t)
+    lo = torch.empty_like(t)
+    st = lib().vocr_split_tf32_f32(ptr(t), ptr(hi), ptr(lo), t.numel(), stream())
+    check(st, "vocr_split_tf32_f32")
+    return hi, lo
+
+
+def tc_gemm(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
+            c_off=0):
+    """Tensor-core GEMM on pre-split operands: A = (hi, lo), B = (hi, lo) (see vocr_tc_gemm_tf32x3)."""
+    st = lib().vocr_tc_gemm_tf32x3(int(a_mn), int(b_mn), M, N, K, _off(A[0], a_off), _off(A[1], a_off), lda,
+                                   _off(B[0], b_off), _off(B[1], b_off), ldb, _off(C, c_off), ldc, ptr(bias),
+                                   int(relu), int(accumulate), stream())
+    check(st, "vocr_tc_gemm_tf32x3")
+
+
 class _Linear(torch.autograd.Function):
     """y = x W^T + b (optionally ReLU); x [M,K], W [N,K] (nn.Linear layout)."""
 
