@@ -46,5 +46,6 @@ def test_split_is_exact(cuda):
     from vistaocr_b200 import ops
     x = torch.randn(100003, device=cuda) * 100
     hi, lo = ops.split_tf32(x)
-    assert torch.equal(hi + lo, x)
-    assert (hi.view(torch.int32) & 0x1fff).abs().max().item() == 0  # hi is exactly representable in TF32
+    assert ((hi + lo) - x).abs().max().item() <= 2.0 ** -21 * x.abs().max().item()  # lo is rounded to TF32 as well
+    assert (hi.view(torch.int32) & 0x1fff).abs().max().item() == 0  # hi, lo exactly representable in TF32
+    assert (lo.view(torch.int32) & 0x1fff).abs().max().item() == 0

@@ -25,7 +25,8 @@ constexpr int kTcThreads = 192;
 constexpr int kTcTileBytes = kTcBM * kTcBK * 4;         // 16 KB
 constexpr int kTcStageBytes = 4 * kTcTileBytes;         // A_hi, A_lo, B_hi, B_lo
 constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemCols = 512;  // 3 rotating hi*hi accumulators + 1 for the lo products, 128 columns each
+constexpr int kTcHiAcc = 3;
 
 struct TcGemmParams {
   float* c;
@@ -58,15 +59,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
 // UMMA shared-memory descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp): start address >> 4 in bits [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type
 // SWIZZLE_128B = 2 in [61,64).  K-major SW128 tile: rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1).
-// MN-major SW128 tile: atoms of (32 elements of M/N) x (8 k rows) = 1024 B; SBO = stride between k groups, LBO = stride
-// between M/N groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major 32-bit operands have exactly one legal layout, SWIZZLE_128B_BASE32B = 1 ("128-B swizzle, 32-B atomicity",
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of (32 elements of M/N = 128 B) x (4 k rows) = 512 B; SBO = stride
+// between 4-row k groups (512 B inside a TMA box of 32 rows), LBO = stride between M/N groups (one 4096-B box).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -145,7 +148,14 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       // per k-step (8 elements of K): K-major advances 32 B inside the swizzle row, MN-major advances one 1024-B atom
       const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
       const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
-      uint32_t accum = 0;
+      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
+      const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
+      // The tensor core truncates (RZ) when it adds into the fp32 accumulator, once per instruction, by up to an ulp
+      // of the RUNNING SUM - a bias that grows linearly with K.  Keep the running sums short and well scaled: the two
+      // lo products go to their own accumulator (its sum is 2^-11 smaller), hi*hi rotates over 3 accumulators by
+      // k-block; the epilogue adds the four in fp32 with round-to-nearest.
+      const uint32_t tmem_lo = tmem_base + kTcHiAcc * kTcBN;
+      uint32_t accum_lo = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
@@ -154,14 +164,15 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
 #pragma unroll
         for (int ks = 0; ks < kTcBK / 8; ++ks) {
-          const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, 1024u);
-          const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, 1024u);
-          const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, 1024u);
-          const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, 1024u);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, accum);  // small terms first
-          accum = 1;
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+          const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
+          const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
+          umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+          accum_lo = 1;
+          umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base + (uint32_t)(kb % kTcHiAcc) * kTcBN, a_hi, b_hi, idesc,
+                    (kb >= kTcHiAcc || ks > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
       }
@@ -176,20 +187,29 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     float* crow = p.c + (size_t)m * p.ldc;
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
 #pragma unroll 1
+    const int n_hi = min(kTcHiAcc, num_kb);  // hi accumulators that were actually written
     for (int cb = 0; cb < kTcBN; cb += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)cb;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float r[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0.f;
+      for (int acc = 0; acc <= n_hi; ++acc) {  // acc == n_hi -> the lo accumulator
+        const int which = (acc == n_hi) ? kTcHiAcc : acc;
+        uint32_t t[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(which * kTcBN + cb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
+              "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]),
+              "=r"(t[16]), "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]),
+              "=r"(t[24]), "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(t[j]);
+      }
       if (m < p.M) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -198,7 +218,7 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
           float v[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float x = __uint_as_float(r[j + q]);
+            float x = r[j + q];
             if (n + q < p.N) {
               if (p.bias) x += __ldg(p.bias + n + q);
               if (p.accumulate) x += crow[n + q];
@@ -225,7 +245,13 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   }
 }
 
-// x -> hi = round-to-nearest TF32 (exactly representable, so the tensor core reads it unchanged), lo = x - hi
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  return __uint_as_float(t);
+}
+// x -> hi = rna_tf32(x), lo = rna_tf32(x - hi): both exactly representable in TF32, so the tensor core (which
+// truncates its inputs) reads them unchanged and the only input error left is the unbiased 2^-23 |x| of rounding lo
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4,
                   long long n) {
@@ -233,19 +259,17 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     float4 h, l;
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+    h.x = rna_tf32(v.x); l.x = rna_tf32(v.x - h.x);
+    h.y = rna_tf32(v.y); l.y = rna_tf32(v.y - h.y);
+    h.z = rna_tf32(v.z); l.z = rna_tf32(v.z - h.z);
+    h.w = rna_tf32(v.w); l.w = rna_tf32(v.w - h.w);
     reinterpret_cast<float4*>(hi)[i] = h;
     reinterpret_cast<float4*>(lo)[i] = l;
   }
   for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x[i]));
-    hi[i] = __uint_as_float(t);
-    lo[i] = x[i] - __uint_as_float(t);
+    const float h = rna_tf32(x[i]);
+    hi[i] = h;
+    lo[i] = rna_tf32(x[i] - h);
   }
 }
 
@@ -272,7 +296,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 tensor [rows][cols] with leading dimension ld (elements); box = {box_cols, box_rows}; 128-B swizzle.
 static bool make_map_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
-                        int box_rows) {
+                        int box_rows, bool mn_major = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -280,7 +304,8 @@ static bool make_map_2d(CUtensorMap* map, const float* base, long long rows, lon
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -316,12 +341,12 @@ extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, cons
   if (!a_mn) {
     ok = ok && make_map_2d(&ma_hi, a_hi, M, K, lda, kTcBK, kTcBM) && make_map_2d(&ma_lo, a_lo, M, K, lda, kTcBK, kTcBM);
   } else {
-    ok = ok && make_map_2d(&ma_hi, a_hi, K, M, lda, 32, kTcBK) && make_map_2d(&ma_lo, a_lo, K, M, lda, 32, kTcBK);
+    ok = ok && make_map_2d(&ma_hi, a_hi, K, M, lda, 32, kTcBK, true) && make_map_2d(&ma_lo, a_lo, K, M, lda, 32, kTcBK, true);
   }
   if (!b_mn) {
     ok = ok && make_map_2d(&mb_hi, b_hi, N, K, ldb, kTcBK, kTcBN) && make_map_2d(&mb_lo, b_lo, N, K, ldb, kTcBK, kTcBN);
   } else {
-    ok = ok && make_map_2d(&mb_hi, b_hi, K, N, ldb, 32, kTcBK) && make_map_2d(&mb_lo, b_lo, K, N, ldb, 32, kTcBK);
+    ok = ok && make_map_2d(&mb_hi, b_hi, K, N, ldb, 32, kTcBK, true) && make_map_2d(&mb_lo, b_lo, K, N, ldb, 32, kTcBK, true);
   }
   if (!ok) return VOCR_EXECUTION_FAILED;
   static bool attr_set = false;
