@@ -59,6 +59,41 @@ def tc_gemm(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, 
     check(st, "vocr_tc_gemm_tf32x3")
 
 
+import os as _os
+
+# Tensor-core (tcgen05 3xTF32) GEMMs are the default; VOCR_TC=0 selects the FFMA engine everywhere (both are this
+# library's kernels - this is an engine choice, not a fallback: shapes the TMA path cannot address, i.e. leading
+# dimensions that are not multiples of 4 floats, always go to the FFMA engine).
+USE_TC = _os.environ.get("VOCR_TC", "1") != "0"
+
+
+class Operand:
+    """A GEMM operand: the fp32 tensor plus, lazily, its (hi, lo) TF32 split (shared by every GEMM that reads it)."""
+
+    def __init__(self, t):
+        self.t = _c(t)
+        self._split = None
+
+    def split(self):
+        if self._split is None:
+            self._split = split_tf32(self.t)
+        return self._split
+
+
+def mm(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
+       c_off=0):
+    """C = op(A) op(B) with vocr_gemm_f32 conventions; A, B are `Operand`s.  Picks the tcgen05 kernel when the
+    operands are TMA-addressable."""
+    ok = USE_TC and lda % 4 == 0 and ldb % 4 == 0 and a_off % 4 == 0 and b_off % 4 == 0 and K >= 1 and \
+        A.t.data_ptr() % 16 == 0 and B.t.data_ptr() % 16 == 0
+    if ok:
+        tc_gemm(transa, 0 if transb else 1, M, N, K, A.split(), lda, B.split(), ldb, C, ldc, bias=bias, relu=relu,
+                accumulate=accumulate, a_off=a_off, b_off=b_off, c_off=c_off)
+    else:
+        gemm(transa, transb, M, N, K, A.t, lda, B.t, ldb, C, ldc, bias=bias, relu=relu, accumulate=accumulate,
+             a_off=a_off, b_off=b_off, c_off=c_off)
+
+
 class _Linear(torch.autograd.Function):
     """y = x W^T + b (optionally ReLU); x [M,K], W [N,K] (nn.Linear layout)."""
 
@@ -69,7 +104,9 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[0]
         y = torch.empty((M, N), dtype=F32, device=x.device)
-        gemm(0, 1, M, N, K, x, K, w, K, y, N, bias=b, relu=relu)
+        xo, wo = Operand(x), Operand(w)
+        mm(0, 1, M, N, K, xo, K, wo, K, y, N, bias=b, relu=relu)
+        ctx.ops = (xo, wo)
         ctx.relu = relu
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.has_bias = b is not None
@@ -84,12 +121,15 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[0]
         dx = dw = db = None
+        xo, wo = ctx.ops
+        ctx.ops = None
+        dyo = Operand(dy)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            gemm(0, 0, M, K, N, dy, N, w, K, dx, K)
+            mm(0, 0, M, K, N, dyo, N, wo, K, dx, K)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            gemm(1, 0, N, K, M, dy, N, x, K, dw, K)
+            mm(1, 0, N, K, M, dyo, N, xo, K, dw, K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((N,), dtype=F32, device=x.device)
             colsum(dy, M, N, N, db)
@@ -281,7 +321,8 @@ class _BiLSTMLayer(torch.autograd.Function):
         H = w_hh.shape[2]
         dev = x.device
         xproj = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev)
-        gemm(0, 1, T * B, 8 * H, Din, x, Din, w_ih, Din, xproj, 8 * H, bias=bias)
+        xo, wo = Operand(x), Operand(w_ih)
+        mm(0, 1, T * B, 8 * H, Din, xo, Din, wo, Din, xproj, 8 * H, bias=bias)
         out = torch.empty((T, B, 2 * H), dtype=F32, device=dev)
         gates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev) if save else None
         cst = torch.empty((T, B, 2, H), dtype=F32, device=dev) if save else None
@@ -295,6 +336,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         if save:
             ctx.save_for_backward(x, w_ih, w_hh, lens_dev, gates, cst, out)
             ctx.tmax = int(tmax)
+            ctx.ops = (xo, wo)
         return out
 
     @staticmethod
@@ -312,21 +354,24 @@ class _BiLSTMLayer(torch.autograd.Function):
         check(st, "vocr_bilstm_bwd_f32")
         dx = dw_ih = dw_hh = db = None
         M = T * B
+        xo, wo = ctx.ops
+        ctx.ops = None
+        dgo, outo = Operand(dgates), Operand(out)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            gemm(0, 0, M, Din, 8 * H, dgates, 8 * H, w_ih, Din, dx, Din)
+            mm(0, 0, M, Din, 8 * H, dgo, 8 * H, wo, Din, dx, Din)
         if ctx.needs_input_grad[1]:
             dw_ih = torch.empty_like(w_ih)
-            gemm(1, 0, 8 * H, Din, M, dgates, 8 * H, x, Din, dw_ih, Din)
+            mm(1, 0, 8 * H, Din, M, dgo, 8 * H, xo, Din, dw_ih, Din)
         if ctx.needs_input_grad[2]:
             # dW_hh[d] = sum_t dgates[t,:,d,:]^T h_prev[t,:,d,:]; h_prev is `out` shifted one step along the
             # direction's time order (rows beyond a sample's length are zero in both operands)
             dw_hh = torch.zeros_like(w_hh)
             if T > 1:
                 K = (T - 1) * B
-                gemm(1, 0, 4 * H, H, K, dgates, 8 * H, out, 2 * H, dw_hh, H, a_off=B * 8 * H, b_off=0, c_off=0)
-                gemm(1, 0, 4 * H, H, K, dgates, 8 * H, out, 2 * H, dw_hh, H, a_off=4 * H, b_off=B * 2 * H + H,
-                     c_off=4 * H * H)
+                mm(1, 0, 4 * H, H, K, dgo, 8 * H, outo, 2 * H, dw_hh, H, a_off=B * 8 * H, b_off=0, c_off=0)
+                mm(1, 0, 4 * H, H, K, dgo, 8 * H, outo, 2 * H, dw_hh, H, a_off=4 * H, b_off=B * 2 * H + H,
+                   c_off=4 * H * H)
         if ctx.needs_input_grad[3]:
             db = torch.empty((8 * H,), dtype=F32, device=dev)
             colsum(dgates, M, 8 * H, 8 * H, db)
