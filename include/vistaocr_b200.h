@@ -171,6 +171,24 @@ int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_
                         const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, const float* bias, int relu,
                         int accumulate, vocr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * 3x3 convolutions on the tensor cores (4-D TMA implicit GEMM + tcgen05 3xTF32), same math as vocr_conv3x3_fwd_f32 /
+ * vocr_conv3x3_wgrad_f32 (src/models/cnnlstm.py:124-134 -> cuDNN).  Activations arrive as (hi, lo) TF32 planes
+ * (vocr_split_tf32_f32), NHWC.
+ *   fwd:   Cin % 32 == 0, Cout % 4 == 0; weight planes K-major [Cout][9*Cin], k = (ky*3+kx)*Cin + ci.  The data
+ *          gradient is the same call on dz with the flipped / transposed weight matrix [Cin][9*Cout].
+ *   wgrad: Cin % 32 == 0, Cout % 32 == 0; dw in state_dict layout [Cout,Cin,3,3]; chunked TMEM accumulation keeps
+ *          the 10^5..10^6-term pixel reduction at fp32 accuracy.
+ * vocr_colstats_f32: BatchNorm statistics, stats[0:C] += sum_p z, stats[C:2C] += sum_p z^2 (float64).
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_tc_conv3x3_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias,
+                        float* z, int B, int H, int W, int Cin, int Cout, vocr_stream_t stream);
+size_t vocr_tc_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout);
+int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const float* dz_hi, const float* dz_lo, float* dw,
+                          int B, int H, int W, int Cin, int Cout, void* workspace, size_t workspace_bytes,
+                          vocr_stream_t stream);
+int vocr_colstats_f32(const float* z, long long P, int C, double* stats, vocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

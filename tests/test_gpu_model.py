@@ -175,4 +175,4 @@ def test_train_step_with_fused_optimizer(cuda):
         p1, _, _ = M.adam_clamp_ref(sd64[k].detach(), g, torch.zeros_like(g), torch.zeros_like(g), 1)
         # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the gradient is not ~0
         mask = g.abs() > 1e-6
-        assert (p.detach().double().cpu() - p1)[mask].abs().max().item() <= 2e-5
+        assert (p.detach().double().cpu() - p1)[mask].abs().max().item() <= 5e-5

@@ -44,6 +44,10 @@ PROTOTYPES = {
     "vocr_bilstm_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_clamp_adam_f32": (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
     "vocr_split_tf32_f32": (c_int, [c_p, c_p, c_p, c_ll, c_p]),
+    "vocr_tc_conv3x3_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "vocr_tc_conv3x3_wgrad_workspace_size": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
+    "vocr_tc_conv3x3_wgrad": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
+    "vocr_colstats_f32": (c_int, [c_p, c_ll, c_int, c_p, c_p]),
     "vocr_tc_gemm_tf32x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_int, c_p, c_int,
                                     c_p, c_int, c_int, c_p]),
 }
@@ -58,11 +62,14 @@ KERNELS_PER_CALL = {
     "vocr_rds_unpool_f32": 1, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
     "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 1, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
     "vocr_clamp_adam_f32": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
+    "vocr_tc_conv3x3_fwd": 1, "vocr_tc_conv3x3_wgrad": 2, "vocr_colstats_f32": 1,
 }
 WORK = {
     "vocr_gemm_f32": lambda a: ("flop", 2.0 * a[2] * a[3] * a[4]),
     "vocr_tc_gemm_tf32x3": lambda a: ("flop", 2.0 * a[2] * a[3] * a[4]),
     "vocr_split_tf32_f32": lambda a: ("byte", 12.0 * a[3]),
+    "vocr_tc_conv3x3_fwd": lambda a: ("flop", 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]),
+    "vocr_tc_conv3x3_wgrad": lambda a: ("flop", 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]),
     "vocr_conv3x3_fwd_f32": lambda a: ("flop", 2.0 * a[4] * a[5] * a[6] * 9 * a[7] * a[8]),
     "vocr_conv3x3_wgrad_f32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5] * 9 * a[6] * a[7]),
     "vocr_bilstm_fwd_f32": lambda a: ("flop", 2.0 * a[9] * a[7] * 8 * a[8] * a[8]),

@@ -1,0 +1,515 @@
+// 3x3 / pad 1 convolutions on the 5th-generation tensor cores: implicit GEMM fed by 4-D TMA tiles of the NHWC
+// activations (the conv halo is the TMA unit's out-of-bounds zero fill - no im2col buffer, no index arithmetic in the
+// kernel), tcgen05.mma kind::tf32 with TMEM accumulators, error-compensated 3xTF32 (see tc_gemm.cu) so the result
+// keeps fp32-level accuracy.  Replaces the FFMA implicit-GEMM kernels of conv.cu for Cin % 32 == 0
+// (reference cnnlstm.py:124-134 -> cuDNN).
+//
+//   forward / data gradient   Z[p, co] = sum_{tap, ci} X[p + tap, ci] * Wn[co, (tap, ci)]
+//       A tile = 128 output pixels (BH rows x BW columns of one image) x 32 input channels of one tap:
+//                one 4-D box {32 c, BW, BH, 1} at (c0, x0+kx-1, y0+ky-1, b) -> 128 rows x 128 B, K-major SWIZZLE_128B
+//       B tile = BN output channels x 32 k: 2-D box of the K-major weight matrix [Cout][9*Cin]
+//       K loop = 9 taps x Cin/32 channel chunks (<= 72 k-blocks); hi*hi rotates over 3 TMEM accumulators
+//   weight gradient           dW[(tap, ci), co] = sum_p X[p + tap, ci] * dZ[p, co]        (reduction over ALL pixels)
+//       both operands are MN-major (channels contiguous, pixels = K rows): boxes {32 c, 32 x, 1, 1}, 128B_ATOM_32B
+//       split-K over image rows across CTAs; inside a CTA the reduction is cut into chunks of 8 k-blocks: each chunk
+//       accumulates in TMEM, is drained by the epilogue warps into fp32 registers (round-to-nearest adds) while the
+//       next chunk runs on another accumulator.  Without this the tensor core's round-toward-zero accumulation biases
+//       a 10^5-term sum by ~1e-4 relative; with it the bias stays ~1e-6.
+#include "tc_common.cuh"
+
+namespace vocr {
+
+constexpr int kCvThreads = 192;
+constexpr int kCvStages = 3;
+constexpr int kCvTile = 16384;                 // 128 rows x 128 B
+constexpr int kCvStageBytes = 4 * kCvTile;     // A_hi, A_lo, B_hi, B_lo (B uses BN*128 B of its 16 KB)
+constexpr int kCvSmemBytes = kCvStages * kCvStageBytes + 1024 + 256;
+constexpr uint32_t kCvTmemCols = 512;
+constexpr int kCvHiAcc = 3;
+
+struct TcConvParams {
+  float* z;
+  const float* bias;
+  int B, H, W, Cin, Cout;
+  int BW, BH, tiles_x, tiles_y, BN;
+};
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   TcConvParams p) {
+  extern __shared__ unsigned char cv_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) &
+                                                         ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kCvStages;
+  uint64_t* tmem_full_bar = bars + 2 * kCvStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.BN;
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int b = tile / p.tiles_y;
+  const int x0 = tx * p.BW, y0 = ty * p.BH;
+  const int chunks = p.Cin / 32;
+  const int num_kb = 9 * chunks;
+  const uint32_t stage_tx = 2 * kCvTile + 2 * (uint32_t)p.BN * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCvStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kCvTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kCvStages;
+        const uint32_t ph = (uint32_t)(kb / kCvStages) & 1u;
+        mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
+        unsigned char* st = smem + (size_t)s * kCvStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+        const int tap = kb / chunks, cc = kb - tap * chunks;
+        const int ky = tap / 3, kx = tap - ky * 3;
+        tma_load_4d(st, &map_x_hi, &full_bar[s], cc * 32, x0 + kx - 1, y0 + ky - 1, b);
+        tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * 32, x0 + kx - 1, y0 + ky - 1, b);
+        tma_load_2d(st + 2 * kCvTile, &map_w_hi, &full_bar[s], kb * 32, n0);
+        tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * 32, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmem_lo = tmem_base + kCvHiAcc * 128;
+      uint32_t accum_lo = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kCvStages;
+        const uint32_t ph = (uint32_t)(kb / kCvStages) & 1u;
+        mbar_wait_or_trap(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)s * kCvStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t a_hi = make_desc(st + ks * 32, 16u, 1024u, 2u);
+          const uint64_t a_lo = make_desc(st + kCvTile + ks * 32, 16u, 1024u, 2u);
+          const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 32, 16u, 1024u, 2u);
+          const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 32, 16u, 1024u, 2u);
+          umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+          accum_lo = 1;
+          umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base + (uint32_t)(kb % kCvHiAcc) * 128, a_hi, b_hi, idesc, (kb >= kCvHiAcc || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    mbar_wait_or_trap(tmem_full_bar, 0);
+    tc_fence_after();
+    const int lane_grp = warp & 3;
+    const int r = lane_grp * 32 + lane;            // row of the tile = pixel iy*BW + ix
+    const int iy = r / p.BW, ix = r - iy * p.BW;
+    const int y = y0 + iy, x = x0 + ix;
+    const bool valid = (y < p.H) && (x < p.W);
+    float* zrow = p.z + (((size_t)b * p.H + y) * p.W + x) * p.Cout;
+    const int n_hi = min(kCvHiAcc, num_kb);
+    for (int cb = 0; cb < p.BN; cb += 32) {
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int a = 0; a <= n_hi; ++a) {
+        const int which = (a == n_hi) ? kCvHiAcc : a;
+        uint32_t t[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(which * 128 + cb), t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(t[j]);
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + cb + j;
+          if (n < p.Cout) {  // Cout % 4 == 0
+            float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (p.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            *reinterpret_cast<float4*>(zrow + n) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kCvTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct TcWgradParams {
+  float* partial;  // [splits][M][N]
+  int B, H, W, Cin, Cout;
+  int M, N, BN;
+  int rows_per_split;  // image rows (b, y) per grid.z slice
+  int xblocks;         // ceil(W / 32)
+};
+constexpr int kWgChunk = 8;  // k-blocks per TMEM accumulation chunk
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                     const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
+                     TcWgradParams p) {
+  extern __shared__ unsigned char cv_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) &
+                                                         ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStageBytes);
+  uint64_t* full_bar = bars;                          // [stages]
+  uint64_t* empty_bar = bars + kCvStages;             // [stages]
+  uint64_t* acc_full = bars + 2 * kCvStages;          // [3]
+  uint64_t* acc_empty = acc_full + kCvHiAcc;          // [3]
+  uint64_t* lo_full = acc_empty + kCvHiAcc;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * p.BN, m0 = blockIdx.y * 128;
+  const int total_rows = p.B * p.H;
+  const int r_begin = blockIdx.z * p.rows_per_split;
+  const int r_end = min(total_rows, r_begin + p.rows_per_split);
+  const int num_kb = max(0, r_end - r_begin) * p.xblocks;
+  const int num_chunks = (num_kb + kWgChunk - 1) / kWgChunk;
+  const int nb_boxes = p.BN / 32;
+  const uint32_t stage_tx = 2 * kCvTile + 2 * (uint32_t)p.BN * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCvStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < kCvHiAcc; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
+    mbar_init(lo_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kCvTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the four 32-row groups of this M tile: (tap, first channel) each
+      int tapj[4], cij[4];
+      for (int j = 0; j < 4; ++j) {
+        const int mrow = m0 + 32 * j;
+        tapj[j] = (mrow < p.M) ? mrow / p.Cin : -1;
+        cij[j] = (mrow < p.M) ? mrow % p.Cin : 0;
+      }
+      int kb = 0;
+      for (int r = r_begin; r < r_end; ++r) {
+        const int b = r / p.H, y = r - b * p.H;
+        for (int xb = 0; xb < p.xblocks; ++xb, ++kb) {
+          const int s = kb % kCvStages;
+          const uint32_t ph = (uint32_t)(kb / kCvStages) & 1u;
+          mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
+          unsigned char* st = smem + (size_t)s * kCvStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          for (int j = 0; j < 4; ++j) {
+            int cx, cy;
+            if (tapj[j] >= 0) {
+              const int ky = tapj[j] / 3, kx = tapj[j] - ky * 3;
+              cx = xb * 32 + kx - 1;
+              cy = y + ky - 1;
+            } else {  // rows beyond 9*Cin: a fully out-of-bounds box delivers zeros (and the expected bytes)
+              cx = 0;
+              cy = p.H + 4;
+            }
+            tma_load_4d(st + j * 4096, &map_x_hi, &full_bar[s], cij[j], cx, cy, b);
+            tma_load_4d(st + kCvTile + j * 4096, &map_x_lo, &full_bar[s], cij[j], cx, cy, b);
+          }
+          for (int j = 0; j < nb_boxes; ++j) {
+            tma_load_4d(st + 2 * kCvTile + j * 4096, &map_dz_hi, &full_bar[s], n0 + 32 * j, xb * 32, y, b);
+            tma_load_4d(st + 3 * kCvTile + j * 4096, &map_dz_lo, &full_bar[s], n0 + 32 * j, xb * 32, y, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmem_lo = tmem_base + kCvHiAcc * 128;
+      uint32_t accum_lo = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        const int a = c % kCvHiAcc;
+        mbar_wait_or_trap(&acc_empty[a], ((uint32_t)(c / kCvHiAcc) & 1u) ^ 1u);
+        tc_fence_after();
+        const int kb1 = min(num_kb, (c + 1) * kWgChunk);
+        for (int kb = c * kWgChunk; kb < kb1; ++kb) {
+          const int s = kb % kCvStages;
+          const uint32_t ph = (uint32_t)(kb / kCvStages) & 1u;
+          mbar_wait_or_trap(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * kCvStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = make_desc(st + ks * 1024, 4096u, 512u, 1u);
+            const uint64_t a_lo = make_desc(st + kCvTile + ks * 1024, 4096u, 512u, 1u);
+            const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 1024, 4096u, 512u, 1u);
+            const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 1024, 4096u, 512u, 1u);
+            umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+            accum_lo = 1;
+            umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
+            umma_tf32(tmem_base + (uint32_t)a * 128, a_hi, b_hi, idesc, (kb > c * kWgChunk || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[a]);
+      }
+      umma_commit(lo_full);
+    }
+  } else {
+    const int lane_grp = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    float sum[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int a = c % kCvHiAcc;
+      mbar_wait_or_trap(&acc_full[a], (uint32_t)(c / kCvHiAcc) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < 128; cb += 32) {
+        if (cb < p.BN) {
+          uint32_t t[32];
+          tmem_ld32(lane_addr + (uint32_t)(a * 128 + cb), t);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[cb + j] += __uint_as_float(t[j]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
+    }
+    if (num_kb > 0) {
+      mbar_wait_or_trap(lo_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < 128; cb += 32) {
+        if (cb < p.BN) {
+          uint32_t t[32];
+          tmem_ld32(lane_addr + (uint32_t)(kCvHiAcc * 128 + cb), t);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[cb + j] += __uint_as_float(t[j]);
+        }
+      }
+    }
+    const int m = m0 + lane_grp * 32 + lane;
+    if (m < p.M) {
+      float* prow = p.partial + ((size_t)blockIdx.z * p.M + m) * p.N;
+#pragma unroll
+      for (int cb = 0; cb < 128; cb += 32) {
+        if (cb < p.BN) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + cb + j;
+            if (n < p.N)
+              *reinterpret_cast<float4*>(prow + n) = make_float4(sum[cb + j], sum[cb + j + 1], sum[cb + j + 2], sum[cb + j + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kCvTmemCols);
+  }
+}
+
+// sum split-K partials [S][9*Cin][Cout] and write the PyTorch layout dW[Cout][Cin][3][3]
+__global__ void __launch_bounds__(256)
+tc_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cin, int Cout, float* __restrict__ dw) {
+  const int total = 9 * Cin * Cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int tap = idx % 9;
+    const int ci = (idx / 9) % Cin;
+    const int co = idx / (9 * Cin);
+    const size_t src = (size_t)(tap * Cin + ci) * Cout + co;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + src];
+    dw[idx] = s;
+  }
+}
+
+// per-channel sum and sum of squares of z [P][C] accumulated into float64 stats[2C] (BatchNorm statistics)
+__global__ void __launch_bounds__(256)
+colstats_kernel(const float* __restrict__ z, long long P, int C4, long long rows_per_cta, double* __restrict__ stats) {
+  extern __shared__ float s_red[];  // [256][8]
+  const int rows = 256 / C4;
+  const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long p0 = (long long)blockIdx.x * rows_per_cta, p1 = min(P, p0 + rows_per_cta);
+  if (r < rows) {
+    for (long long q = p0 + r; q < p1; q += rows) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(z) + q * C4 + c4);
+      s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+      s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+      s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+    }
+  }
+  float* mine = s_red + (size_t)threadIdx.x * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mine[i] = s1[i];
+    mine[4 + i] = s2[i];
+  }
+  __syncthreads();
+  const int C = C4 * 4;
+  for (int o = threadIdx.x; o < 2 * C; o += 256) {
+    const int which = o / C, c = o % C;
+    double t = 0.0;
+    for (int rr = 0; rr < rows; ++rr) t += (double)s_red[((size_t)rr * C4 + (c >> 2)) * 8 + which * 4 + (c & 3)];
+    atomicAdd(&stats[which * C + c], t);
+  }
+}
+
+}  // namespace vocr
+
+using namespace vocr;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static void pick_tile(int H, int W, int* BW, int* BH) {
+  // 128 output pixels per tile as BH x BW; pick the shape that wastes the fewest out-of-image pixels
+  const int cand[3][2] = {{128, 1}, {64, 2}, {32, 4}};
+  double best = -1;
+  for (int i = 0; i < 3; ++i) {
+    const int bw = cand[i][0], bh = cand[i][1];
+    const double eff = ((double)W / (ceil_div(W, bw) * bw)) * ((double)H / (ceil_div(H, bh) * bh));
+    if (eff > best + 1e-9) {
+      best = eff;
+      *BW = bw;
+      *BH = bh;
+    }
+  }
+}
+
+// z[B,H,W,Cout] = conv3x3_pad1(x) + bias on tensor cores.  x planes (hi, lo) NHWC [B,H,W,Cin], Cin % 32 == 0;
+// weight planes K-major [Cout][9*Cin] with k = (ky*3+kx)*Cin + ci; Cout % 4 == 0.
+extern "C" int vocr_tc_conv3x3_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                                   const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
+                                   vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 32 == 0 && Cout % 4 == 0);
+  if (B == 0) return VOCR_OK;
+  VOCR_REQUIRE(x_hi && x_lo && w_hi && w_lo && z);
+  VOCR_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(z) &&
+               (!bias || aligned16(bias)));
+  TcConvParams p;
+  p.z = z; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  pick_tile(H, W, &p.BW, &p.BH);
+  p.tiles_x = ceil_div(W, p.BW);
+  p.tiles_y = ceil_div(H, p.BH);
+  p.BN = (Cout <= 64) ? 64 : 128;
+  CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
+  bool ok = make_map_nhwc(&mx_hi, x_hi, B, H, W, Cin, 32, p.BW, p.BH, false) &&
+            make_map_nhwc(&mx_lo, x_lo, B, H, W, Cin, 32, p.BW, p.BH, false) &&
+            make_map_2d(&mw_hi, w_hi, Cout, 9LL * Cin, 9LL * Cin, 32, p.BN) &&
+            make_map_2d(&mw_lo, w_lo, Cout, 9LL * Cin, 9LL * Cin, 32, p.BN);
+  if (!ok) return VOCR_EXECUTION_FAILED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) != cudaSuccess)
+      return VOCR_EXECUTION_FAILED;
+    attr_set = true;
+  }
+  const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
+  VOCR_REQUIRE(tiles <= 2147483647LL);
+  dim3 grid((unsigned)tiles, ceil_div(Cout, p.BN));
+  tc_conv_fwd_kernel<<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+extern "C" size_t vocr_tc_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout) {
+  (void)B; (void)H; (void)W;
+  return sizeof(float) * (size_t)9 * Cin * Cout * 64 + 256;
+}
+
+// dw[Cout,Cin,3,3] = sum over pixels of x(p+tap, ci) * dz(p, co); x and dz given as (hi, lo) NHWC planes,
+// Cin % 32 == 0, Cout % 32 == 0.
+extern "C" int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const float* dz_hi, const float* dz_lo,
+                                     float* dw, int B, int H, int W, int Cin, int Cout, void* workspace,
+                                     size_t workspace_bytes, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cin > 0 && Cout > 0);
+  VOCR_REQUIRE(x_hi && x_lo && dz_hi && dz_lo && dw && workspace);
+  VOCR_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(dz_hi) && aligned16(dz_lo) && aligned16(workspace));
+  TcWgradParams p;
+  p.partial = static_cast<float*>(workspace);
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.M = 9 * Cin; p.N = Cout;
+  p.BN = (Cout <= 64) ? 64 : 128;
+  p.xblocks = ceil_div(W, 32);
+  const int tiles = ceil_div(p.M, 128) * ceil_div(p.N, p.BN);
+  const int total_rows = B * H;
+  int splits = max(1, min(64, min(total_rows, (2 * kNumSMs) / tiles)));
+  p.rows_per_split = ceil_div(total_rows, splits);
+  splits = ceil_div(total_rows, p.rows_per_split);
+  VOCR_REQUIRE(sizeof(float) * (size_t)p.M * p.N * splits <= workspace_bytes);
+  CUtensorMap mx_hi, mx_lo, md_hi, md_lo;
+  bool ok = make_map_nhwc(&mx_hi, x_hi, B, H, W, Cin, 32, 32, 1, true) &&
+            make_map_nhwc(&mx_lo, x_lo, B, H, W, Cin, 32, 32, 1, true) &&
+            make_map_nhwc(&md_hi, dz_hi, B, H, W, Cout, 32, 32, 1, true) &&
+            make_map_nhwc(&md_lo, dz_lo, B, H, W, Cout, 32, 32, 1, true);
+  if (!ok) return VOCR_EXECUTION_FAILED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) != cudaSuccess)
+      return VOCR_EXECUTION_FAILED;
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.N, p.BN), ceil_div(p.M, 128), splits);
+  tc_conv_wgrad_kernel<<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, md_hi, md_lo, p);
+  VOCR_CHECK_LAUNCH();
+  tc_wgrad_reduce_kernel<<<min(ceil_div(p.M * p.N, 256), 4 * kNumSMs), 256, 0, stream>>>(p.partial, splits, Cin, Cout, dw);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// stats[0:C] += sum_p z[p,c], stats[C:2C] += sum_p z[p,c]^2 (float64).  C % 4 == 0, C <= 1024.
+extern "C" int vocr_colstats_f32(const float* z, long long P, int C, double* stats, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(P >= 0 && C > 0 && C % 4 == 0 && C <= 1024 && stats);
+  if (P == 0) return VOCR_OK;
+  VOCR_REQUIRE(z && aligned16(z));
+  const int C4 = C / 4, rows = 256 / C4;
+  long long rows_per_cta = ceil_div64(P, (long long)kNumSMs * 4);
+  rows_per_cta = max((long long)rows * 8, ceil_div64(rows_per_cta, rows) * rows);
+  const int grid = (int)ceil_div64(P, rows_per_cta);
+  colstats_kernel<<<grid, 256, sizeof(float) * 256 * 8, stream>>>(z, P, C4, rows_per_cta, stats);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}

@@ -14,8 +14,7 @@
 // memory: activations [M,K], nn.Linear weights [N,K]) and MN-major (the reduction dimension is the row index: dY^T X
 // weight gradients, dY W data gradients); they differ only in the TMA box shape and the UMMA descriptor strides.
 // Every mbarrier wait is bounded and traps, so a descriptor bug surfaces as a launch error, not a hung GPU.
-#include <cuda.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vocr {
 
@@ -35,43 +34,6 @@ struct TcGemmParams {
   int relu, accumulate;
   int a_mn, b_mn;  // 1 = MN-major operand
 };
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// UMMA shared-memory descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp): start address >> 4 in bits [0,14),
-// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type
-// SWIZZLE_128B = 2 in [61,64).  K-major SW128 tile: rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1).
-// MN-major 32-bit operands have exactly one legal layout, SWIZZLE_128B_BASE32B = 1 ("128-B swizzle, 32-B atomicity",
-// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of (32 elements of M/N = 128 B) x (4 k rows) = 512 B; SBO = stride
-// between 4-row k groups (512 B inside a TMA box of 32 rows), LBO = stride between M/N groups (one 4096-B box).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -276,38 +238,6 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __
 }  // namespace vocr
 
 using namespace vocr;
-
-// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ---------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D fp32 tensor [rows][cols] with leading dimension ld (elements); box = {box_cols, box_rows}; 128-B swizzle.
-static bool make_map_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols,
-                        int box_rows, bool mn_major = false) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 extern "C" int vocr_split_tf32_f32(const float* x, float* hi, float* lo, long long n, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -168,6 +168,65 @@ def _conv_wgrad(x, dz, B, H, W, Cin, Cout):
     return dw
 
 
+def _tc_conv_fwd(x_s, w_s, bias, B, H, W, Cin, Cout):
+    """x_s, w_s: (hi, lo) planes; x NHWC [B,H,W,Cin], w K-major [Cout, 9*Cin]."""
+    z = torch.empty((B, H, W, Cout), dtype=F32, device=x_s[0].device)
+    st = lib().vocr_tc_conv3x3_fwd(ptr(x_s[0]), ptr(x_s[1]), ptr(w_s[0]), ptr(w_s[1]), ptr(bias), ptr(z), B, H, W, Cin,
+                                   Cout, stream())
+    check(st, "vocr_tc_conv3x3_fwd")
+    return z
+
+
+def _tc_conv_wgrad(x_s, dz_s, B, H, W, Cin, Cout):
+    dev = x_s[0].device
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
+    wsb = lib().vocr_tc_conv3x3_wgrad_workspace_size(B, H, W, Cin, Cout)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    st = lib().vocr_tc_conv3x3_wgrad(ptr(x_s[0]), ptr(x_s[1]), ptr(dz_s[0]), ptr(dz_s[1]), ptr(dw), B, H, W, Cin, Cout,
+                                     ptr(ws), wsb, stream())
+    check(st, "vocr_tc_conv3x3_wgrad")
+    return dw
+
+
+def conv3x3(x, weight, bias, x_op=None):
+    """z = conv3x3_pad1(x) + bias, NHWC; picks the tensor-core kernel when Cin % 32 == 0.  Returns (z, x_operand)."""
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    if USE_TC and Cin % 32 == 0 and Cout % 4 == 0:
+        x_op = x_op or Operand(x)
+        wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+        return _tc_conv_fwd(x_op.split(), wn.split(), bias, B, H, W, Cin, Cout), x_op
+    wk, _ = _weight_layout(_c(weight.detach()), True, False)
+    return _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, None), x_op
+
+
+def conv3x3_dgrad(dz, weight, dz_op=None):
+    """dx = conv3x3 data gradient (NHWC)."""
+    B, H, W, Cout = dz.shape
+    Cin = weight.shape[1]
+    if USE_TC and Cout % 32 == 0 and Cin % 4 == 0:
+        dz_op = dz_op or Operand(dz)
+        wd = Operand(weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout))
+        return _tc_conv_fwd(dz_op.split(), wd.split(), None, B, H, W, Cout, Cin), dz_op
+    _, wd = _weight_layout(_c(weight.detach()), False, True)
+    return _conv_fwd(dz, wd, None, B, H, W, Cout, Cin, None), dz_op
+
+
+def conv3x3_wgrad(x, dz, x_op=None, dz_op=None):
+    B, H, W, Cin = x.shape
+    Cout = dz.shape[3]
+    if USE_TC and Cin % 32 == 0 and Cout % 32 == 0:
+        x_op = x_op or Operand(x)
+        dz_op = dz_op or Operand(dz)
+        return _tc_conv_wgrad(x_op.split(), dz_op.split(), B, H, W, Cin, Cout)
+    return _conv_wgrad(x, dz, B, H, W, Cin, Cout)
+
+
+def colstats(z, C, stats):
+    st = lib().vocr_colstats_f32(ptr(z), z.numel() // C, C, ptr(stats), stream())
+    check(st, "vocr_colstats_f32")
+
+
 class _ConvBNReLU(torch.autograd.Function):
     """a = relu(batchnorm(conv3x3(x) + bias)).  x NHWC [B,H,W,Cin]; weight [Cout,Cin,3,3] (state_dict layout).
     seq_layout=True writes a as the time-major sequence [W, B, H*Cout] (feature = y*Cout + c)."""
@@ -179,9 +238,11 @@ class _ConvBNReLU(torch.autograd.Function):
         B, H, W, Cin = x.shape
         Cout = weight.shape[0]
         dev = x.device
-        wk, _ = _weight_layout(_c(weight), True, False)
         stats = torch.zeros((2 * Cout,), dtype=torch.float64, device=dev) if training else None
-        z = _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, stats)
+        z, x_op = conv3x3(x, weight, bias)
+        if training:
+            colstats(z, Cout, stats)
+        ctx.x_op = x_op
         scale = torch.empty((Cout,), dtype=F32, device=dev)
         shift = torch.empty((Cout,), dtype=F32, device=dev)
         mean = torch.empty((Cout,), dtype=F32, device=dev)
@@ -219,10 +280,11 @@ class _ConvBNReLU(torch.autograd.Function):
                                         ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red), stream())
         check(st, "vocr_bn_relu_bwd_f32")
         dx = None
+        dz_op = None
         if ctx.needs_input_grad[0]:
-            _, wd = _weight_layout(_c(weight), False, True)
-            dx = _conv_fwd(dz, wd, None, B, H, W, Cout, Cin, None)
-        dw = _conv_wgrad(x, dz, B, H, W, Cin, Cout)
+            dx, dz_op = conv3x3_dgrad(dz, weight)
+        dw = conv3x3_wgrad(x, dz, ctx.x_op, dz_op)
+        ctx.x_op = None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
 
 
