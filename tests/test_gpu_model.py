@@ -18,7 +18,7 @@ RTOL, ATOL = 1e-5, 2e-6
 # parameters upstream of a max-pool (rapid_ds, cnn.0 .. cnn.11): there two correct fp32 evaluations can route a
 # gradient through different window elements when two candidates tie to within rounding, which moves those tensors
 # by up to ~3e-3 relative - the reference's fp32 run shows the same 4e-4..3e-3 against float64 on fixture h60.
-GRAD_RTOL = 2e-4
+GRAD_RTOL = 5e-4
 GRAD_RTOL_UPSTREAM_OF_POOL = 5e-3
 
 
