@@ -104,6 +104,9 @@ int vocr_rds_fwd_f32(const float* x, const float* wk, const float* bias, float* 
                      int Cin, vocr_stream_t stream);
 int vocr_rds_unpool_f32(const float* dy, const float* y, const uint8_t* arg, float* dpre, int B, int H, int W,
                         vocr_stream_t stream);
+/* first stage (Cin = 1, no data gradient): dw[16,1,3,3] and db[16] straight from the pooled gradient; ws: double[160] */
+int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const uint8_t* arg, float* dw, float* db,
+                          int B, int H, int W, double* ws, vocr_stream_t stream);
 
 /* BatchNorm2d(eps, momentum) + ReLU (src/models/cnnlstm.py:263-266).
  * vocr_bn_finalize_f32: training != 0: batch statistics from stats (see conv fwd) over `count` pixels, running

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "vocr_conv3x3_wgrad_f32": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_rds_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
     "vocr_rds_unpool_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
+    "vocr_rds_wgrad_c1_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     "vocr_bn_finalize_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_f, c_f, c_int, c_p, c_p, c_p, c_p, c_int, c_p]),
     "vocr_bn_relu_apply_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_p]),
     "vocr_bn_relu_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll,
@@ -59,7 +60,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "vocr_greedy_decode_f32": 2, "vocr_ctc_loss_f32": 4, "vocr_gemm_f32": 1, "vocr_colsum_f32": 1,
     "vocr_conv_weight_layout_f32": 1, "vocr_conv3x3_fwd_f32": 1, "vocr_conv3x3_wgrad_f32": 2, "vocr_rds_fwd_f32": 1,
-    "vocr_rds_unpool_f32": 1, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
+    "vocr_rds_unpool_f32": 1, "vocr_rds_wgrad_c1_f32": 2, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
     "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 1, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
     "vocr_clamp_adam_f32": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
     "vocr_tc_conv3x3_fwd": 1, "vocr_tc_conv3x3_wgrad": 2, "vocr_colstats_f32": 1,

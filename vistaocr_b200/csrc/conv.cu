@@ -340,6 +340,97 @@ rds_unpool_kernel(const float* __restrict__ dy, const float* __restrict__ y, con
   *reinterpret_cast<float4*>(dpre + (size_t)pp * kRdsCout + cq * 4) = g;
 }
 
+// Weight / bias gradient of the FIRST rapid-downsample stage (Cin = 1, no data gradient needed), straight from the
+// pooled gradient: only the window position that won the max-pool (and survived the ReLU) carries gradient, so the
+// dense full-resolution dpre tensor is never built.  One thread = one pooled pixel x 4 output channels; per-thread
+// partials (4 x 9 weights + 4 biases) are reduced by warp shuffles, then shared memory, then float64 atomics.
+__global__ void __launch_bounds__(256)
+rds_wgrad_c1_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                    const uint8_t* __restrict__ arg, int B, int H, int W, double* __restrict__ out /*[16*9 + 16]*/) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * 4;
+  float acc[4][9], accb[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    accb[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+  }
+  // grid-stride in units that keep tid & 3 == channel quad fixed per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += stride) {
+    const int cq = (int)(gid & 3);
+    const long long pp = gid >> 2;
+    const int xo = (int)(pp % Wo);
+    const int yo = (int)((pp / Wo) % Ho);
+    const int b = (int)(pp / ((long long)Wo * Ho));
+    const size_t o = (size_t)pp * kRdsCout + cq * 4;
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + o));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y + o));
+    const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(arg + o));
+    const float g[4] = {v.x > 0.f ? d.x : 0.f, v.y > 0.f ? d.y : 0.f, v.z > 0.f ? d.z : 0.f, v.w > 0.f ? d.w : 0.f};
+    float patch[4][4];
+    const int y0 = yo * 2 - 1, x0 = xo * 2 - 1;
+    const float* xb = x + (size_t)b * H * W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int yy = y0 + r, xc = x0 + c;
+        patch[r][c] = (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(xb + (size_t)yy * W + xc) : 0.f;
+      }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int pos = (int)((am >> (8 * c)) & 0xff);
+      accb[c] += g[c];
+#pragma unroll
+      for (int pv = 0; pv < 4; ++pv) {
+        const float gg = (pos == pv) ? g[c] : 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc[c][ky * 3 + kx] = fmaf(gg, patch[(pv >> 1) + ky][(pv & 1) + kx], acc[c][ky * 3 + kx]);
+      }
+    }
+  }
+  // lanes with equal (lane & 3) hold the same channel quad: reduce over lane bits 2..4
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) accb[c] += __shfl_xor_sync(0xffffffffu, accb[c], off);
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], off);
+  }
+  __shared__ float s_part[8][4][40];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) s_part[warp][lane][c * 9 + t] = acc[c][t];
+      s_part[warp][lane][36 + c] = accb[c];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+    const int cq = i / 40, k = i % 40;
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)s_part[w][cq][k];
+    // out layout: dw[co][tap] (144) then db[co] (16)
+    if (k < 36) atomicAdd(&out[(cq * 4 + k / 9) * 9 + k % 9], t);
+    else atomicAdd(&out[144 + cq * 4 + (k - 36)], t);
+  }
+}
+
+__global__ void f64_to_f32_conv_kernel(const double* __restrict__ in, float* __restrict__ a, int na,
+                                       float* __restrict__ b, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < na) a[i] = (float)in[i];
+  else if (i < na + nb) b[i - na] = (float)in[i];
+}
+
 }  // namespace vocr
 
 using namespace vocr;
@@ -439,6 +530,24 @@ extern "C" int vocr_rds_unpool_f32(const float* dy, const float* y, const uint8_
   if (total == 0) return VOCR_OK;
   VOCR_REQUIRE(dy && y && arg && dpre);
   rds_unpool_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(dy, y, arg, dpre, B, H, W);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// First rapid-downsample stage (Cin = 1): dw[16,1,3,3], db[16] from the pooled gradient.  ws: float64[160] scratch.
+extern "C" int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const uint8_t* arg, float* dw,
+                                     float* db, int B, int H, int W, double* ws, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H >= 2 && W >= 2 && dw && db && ws);
+  if (cudaMemsetAsync(ws, 0, sizeof(double) * 160, stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+  const long long total = (long long)B * (H / 2) * (W / 2) * 4;
+  if (total > 0) {
+    VOCR_REQUIRE(x && dy && y && arg);
+    const int grid = (int)min((long long)kNumSMs * 8, ceil_div64(total, 256));
+    rds_wgrad_c1_kernel<<<grid, 256, 0, stream>>>(x, dy, y, arg, B, H, W, ws);
+    VOCR_CHECK_LAUNCH();
+  }
+  f64_to_f32_conv_kernel<<<1, 192, 0, stream>>>(ws, dw, 144, db, 16);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }

@@ -319,6 +319,14 @@ class _RapidDS(torch.autograd.Function):
         B, H, W, Cin = x.shape
         dev = x.device
         dy = _c(dy)
+        if Cin == 1 and not ctx.needs_input_grad[0]:
+            dw = torch.empty((16, 1, 3, 3), dtype=F32, device=dev)
+            db = torch.empty((16,), dtype=F32, device=dev)
+            ws = torch.empty((160,), dtype=torch.float64, device=dev)
+            st = lib().vocr_rds_wgrad_c1_f32(ptr(x), ptr(dy), ptr(y), ptr(arg), ptr(dw), ptr(db), B, H, W, ptr(ws),
+                                             stream())
+            check(st, "vocr_rds_wgrad_c1_f32")
+            return None, dw, db
         dpre = torch.empty((B, H, W, 16), dtype=F32, device=dev)
         st = lib().vocr_rds_unpool_f32(ptr(dy), ptr(y), ptr(arg), ptr(dpre), B, H, W, stream())
         check(st, "vocr_rds_unpool_f32")
