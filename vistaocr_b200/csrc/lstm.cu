@@ -1,34 +1,39 @@
 // Bidirectional LSTM layer recurrence on sm_100a, forward and backward, as PERSISTENT cooperative kernels
 // (reference cnnlstm.py:148-149,285-290: nn.LSTM on a packed sequence -> cuDNN RNN).
 //
-// The input projections x_t W_ih^T + b_ih + b_hh of ALL timesteps and both directions are one GEMM done beforehand
-// (xproj [T,B,2,4H]); what is left is the strictly sequential part  h_{t-1} W_hh^T  + gate nonlinearities.
-// Work decomposition: an "instance" = (direction, tile of 32 samples); it is served by NSL CTAs ("slices"), each
-// owning US hidden units = 4*US rows of W_hh, which stay RESIDENT IN SHARED MEMORY for all timesteps
-// (H=512: 32 slices x 64 rows x 512 fp32 = 129 KB each).  Per step a slice multiplies the 32 x H tile of h_{t-1}
-// by its 64 rows (K split 4 ways across warps, reduced through shared memory), applies the gates for its units,
-// and publishes its 32 x US piece of h_t through a ping-pong buffer in global memory (L2); the slices of an
-// instance meet at a monotonically increasing flag (release/acquire at gpu scope).  Directions and batch tiles never
-// synchronise with each other, so both directions run concurrently (2 dirs x 2 tiles x 32 slices = 128 CTAs for
-// B=64, H=512, one per SM).  Ragged lengths use packed-sequence semantics by masking: sample b is active at step k
-// iff k < lens[b]; the reverse direction visits t = lens[b]-1-k, i.e. starts at the sample's own last frame;
-// outputs beyond lens[b] stay zero.
+// The input projections x_t W_ih^T + b_ih + b_hh of ALL timesteps and both directions are one tensor-core GEMM done
+// beforehand (xproj [T,B,2,4H]); what is left is the strictly sequential part  h_{t-1} W_hh^T  + gate nonlinearities.
 //
-// Backward keeps the same residency: a slice turns dh into gate gradients for its own units, multiplies them by its
-// W_hh rows (32 x 64 by 64 x H) into a partial dh_{t-1} for ALL units, and the instance reduce-scatters the partials
-// through L2 in a fixed order (deterministic).  dW_hh / dW_ih / db / dx are plain GEMMs over the saved gate
-// gradients afterwards (host side).
+// Work decomposition.  An "instance" = (direction, tile of 16 samples); it is served by NSL CTAs ("slices"), each
+// owning US hidden units = 4*US rows of W_hh, which stay RESIDENT IN SHARED MEMORY (fp32) for all timesteps
+// (H=512: 32 slices x 64 rows x 512 = 129 KB each).  Per step a slice multiplies the 16 x H tile of h_{t-1} by its
+// 64 rows on the tensor cores (mma.sync m16n8k8 TF32 with the 3xTF32 hi/lo split done in registers, so the product
+// keeps fp32-level accuracy without doubling the resident weights; K split over 4 warp pairs and reduced through
+// shared memory), applies the gates for its units, and publishes its 16 x US piece of h_t through a ping-pong buffer
+// in global memory (L2); the slices of an instance meet at a monotonically increasing flag (release/acquire at gpu
+// scope) - there is no grid-wide barrier.
+// Latency hiding: every CTA serves TWO instances (two sample tiles of one direction) in alternation, so the L2 round
+// trip of one tile's h exchange (flag + 32 KB load) overlaps the other tile's product and gate math.
+// B=64, H=512: 2 directions x 2 tile pairs x 32 slices = 128 CTAs, one per SM, both directions concurrent.
+// Ragged lengths use packed-sequence semantics by masking: sample b is active at step k iff k < lens[b]; the reverse
+// direction visits t = lens[b]-1-k, i.e. starts at the sample's own last frame; outputs beyond lens[b] stay zero.
+//
+// Backward keeps the same residency and interleaving: a slice turns dh into gate gradients for its own units,
+// multiplies them by its W_hh rows (16 x 64 by 64 x H, tensor cores) into a partial dh_{t-1} for ALL units, and the
+// instance reduce-scatters the partials through L2 in a fixed order (deterministic).  dW_hh / dW_ih / db / dx are
+// tensor-core GEMMs over the saved gate gradients afterwards (host side, vistaocr_b200/ops.py).
 #include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace vocr {
 
 constexpr int kLstmThreads = 256;
-constexpr int kLstmBT = 32;        // samples per instance
+constexpr int kLstmBT = 16;        // samples per instance = MMA M
+constexpr int kLstmNI = 2;         // instances interleaved per CTA
 constexpr int kLstmMaxUS = 16;     // hidden units per slice
-constexpr int kLstmRows = 64;      // 4 * kLstmMaxUS gate rows per slice (padded)
-constexpr int kLstmPairs = 2;      // (sample, unit) pairs per thread: 32*16/256
-constexpr int kLstmPartLd = kLstmRows + 4;  // padded row of the K-split partial sums (conflict-free stores)
+constexpr int kLstmRows = 64;      // 4 * kLstmMaxUS gate rows per slice (zero padded)
+constexpr int kLstmPartLd = 72;    // row stride of the K-split partial sums [4][16][72]
+constexpr int kLstmDaLd = kLstmRows + 4;
 
 struct LstmArgs {
   const float* xproj;   // [T,B,2,4H]  (fwd)            | dout [T,B,2H] (bwd)
@@ -37,9 +42,9 @@ struct LstmArgs {
   float* out;           // [T,B,2H]    (fwd, pre-zeroed) | dgates [T,B,2,4H] (bwd, pre-zeroed)
   float* gates;         // [T,B,2,4H] activated i,f,g,o (fwd: written if non-null; bwd: read)
   float* cst;           // [T,B,2,H]  cell state        (fwd: written if non-null; bwd: read)
-  float* xchg;          // fwd: [n_inst][2][32][Hp]      | bwd: [n_inst][2][NSL][32][Hp]
+  float* xchg;          // fwd: [n_inst][2][16][Hp]      | bwd: [n_inst][2][NSL][16][Hp]
   unsigned* flags;      // [n_inst], zeroed before launch
-  int T, B, H, Hp, US, NSL, Tmax, NBT, n_inst;
+  int T, B, H, Hp, US, NSL, Tmax, NBT, gpd, n_groups;  // gpd = instance pairs per direction
 };
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -50,7 +55,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void red_release(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-// all slices of an instance have published step data `target/NSL` times
 __device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned target) {
   if (threadIdx.x == 0) {
     unsigned spins = 0;
@@ -71,8 +75,19 @@ __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- tensor-core helpers: m16n8k8 TF32, operands split hi/lo in registers (3xTF32) ---------------------------------
+__device__ __forceinline__ void split2(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));  // the tensor core ignores the 13 low mantissa bits of lo
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 
 // load this slice's W_hh rows into shared memory: Ws[r = g*US + u][k], zero padded to 64 rows x (Hp+4)
 __device__ __forceinline__ void load_w_slice(float* Ws, const float* __restrict__ whh_dir, int H, int Hp, int US,
@@ -87,138 +102,143 @@ __device__ __forceinline__ void load_w_slice(float* Ws, const float* __restrict_
   }
 }
 
+__host__ __device__ inline int lstm_hs_floats(int Hp) {
+  const int a = kLstmBT * (Hp + 4), b = 4 * kLstmBT * kLstmPartLd;
+  return a > b ? a : b;
+}
+
 // ================================================ forward =====================================================
 __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a) {
   extern __shared__ __align__(16) float lstm_smem[];
   const int H = a.H, Hp = a.Hp, US = a.US, ld = Hp + 4;
-  float* Ws = lstm_smem;                 // [64][ld]
-  float* hs = Ws + kLstmRows * ld;       // [32][ld]   (aliased by part[4][32][68] after the product)
-  float* part = hs;
+  float* Ws = lstm_smem;                          // [64][ld]
+  float* hbuf = Ws + kLstmRows * ld;              // [NI][hs_floats]: h tile, later aliased by the K-split partials
+  const int hs_floats = lstm_hs_floats(Hp);
   const int slice = blockIdx.x;
   const int u0 = slice * US;
   const int nu = min(US, H - u0);
-  const int tid = threadIdx.x;
-  // product mapping: 4 K-groups x 64 threads; thread -> samples tb+8i (i<4), rows tr+8j (j<8)
-  const int kg = tid >> 6, t64 = tid & 63, tb = t64 & 7, tr = t64 >> 3;
-  const int kq = Hp / 4;  // K range of a group (Hp % 16 == 0)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;          // mma fragment coordinates
+  const int kgrp = warp >> 1, nh = warp & 1;      // K quarter, half of the 64 gate rows
+  const int kq = Hp / 4;                          // K range of a quarter (Hp % 32 == 0 -> multiple of 8)
+  // gate epilogue: one (sample, unit) pair per thread and instance
+  const int pb = tid / US, pu = tid - pb * US;
 
-  for (int inst = blockIdx.y; inst < a.n_inst; inst += gridDim.y) {
-    const int dir = inst / a.NBT, bt = inst - dir * a.NBT;
-    const int b0 = bt * kLstmBT;
-    const int nb = min(kLstmBT, a.B - b0);
+  for (int grp = blockIdx.y; grp < a.n_groups; grp += gridDim.y) {
+    const int dir = grp / a.gpd, pair = grp - dir * a.gpd;
+    const int ni = min(kLstmNI, a.NBT - kLstmNI * pair);
     __syncthreads();
     load_w_slice(Ws, a.whh + (size_t)dir * 4 * H * H, H, Hp, US, u0, nu);
-    float* hx = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
-    unsigned* flag = a.flags + inst;
-
-    // (sample, unit) pairs owned by this thread for the gate epilogue
-    int pb[kLstmPairs], pu[kLstmPairs], plen[kLstmPairs];
-    float c_reg[kLstmPairs], h_reg[kLstmPairs];
+    int b0[kLstmNI], plen[kLstmNI];
+    float* hx[kLstmNI];
+    unsigned* flag[kLstmNI];
+    float c_reg[kLstmNI], h_reg[kLstmNI];
+    bool pok[kLstmNI];
 #pragma unroll
-    for (int i = 0; i < kLstmPairs; ++i) {
-      const int p = tid + i * kLstmThreads;
-      pb[i] = p / US;
-      pu[i] = p - pb[i] * US;
-      const bool ok = pb[i] < nb && pu[i] < nu && pb[i] < kLstmBT;
-      plen[i] = ok ? min(a.lens[b0 + pb[i]], a.Tmax) : 0;
-      if (!ok) pb[i] = -1;
+    for (int i = 0; i < kLstmNI; ++i) {
+      const int inst = dir * a.NBT + kLstmNI * pair + i;
+      b0[i] = (kLstmNI * pair + i) * kLstmBT;
+      const int nb = min(kLstmBT, a.B - b0[i]);
+      pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
+      plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
+      hx[i] = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
+      flag[i] = a.flags + inst;
       c_reg[i] = 0.f;
       h_reg[i] = 0.f;
     }
     __syncthreads();
 
     for (int k = 0; k < a.Tmax; ++k) {
-      // prefetch this step's input projections (independent of the recurrence)
-      float xp[kLstmPairs][4];
-      int tt[kLstmPairs];
 #pragma unroll
-      for (int i = 0; i < kLstmPairs; ++i) {
-        const bool act = pb[i] >= 0 && k < plen[i];
-        tt[i] = act ? (dir == 0 ? k : plen[i] - 1 - k) : -1;
+      for (int i = 0; i < kLstmNI; ++i) {
+        if (i >= ni) continue;
+        float* hs = hbuf + (size_t)i * hs_floats;
+        // this step's input projections (independent of the recurrence): issue the loads before the wait
+        const bool act = pok[i] && k < plen[i];
+        const int tt = act ? (dir == 0 ? k : plen[i] - 1 - k) : -1;
+        float xp[4] = {0.f, 0.f, 0.f, 0.f};
         if (act) {
-          const float* xr = a.xproj + (((size_t)tt[i] * a.B + b0 + pb[i]) * 2 + dir) * 4 * H + u0 + pu[i];
+          const float* xr = a.xproj + (((size_t)tt * a.B + b0[i] + pb) * 2 + dir) * 4 * H + u0 + pu;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) xp[i][g] = __ldg(xr + (size_t)g * H);
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) xp[i][g] = 0.f;
+          for (int q = 0; q < 4; ++q) xp[q] = __ldg(xr + (size_t)q * H);
         }
-      }
-      float acc[4][8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-      if (k > 0) {
-        wait_flag(flag, (unsigned)(a.NSL * k));
-        const float* src = hx + (size_t)((k - 1) & 1) * kLstmBT * Hp;
-        const int chunks = kLstmBT * (Hp / 4);
-        for (int i = tid; i < chunks; i += kLstmThreads) {
-          const int r = i / (Hp / 4), c4 = i - r * (Hp / 4);
-          cp_async16_cg(hs + (size_t)r * ld + c4 * 4, src + (size_t)r * Hp + c4 * 4);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        const float* hrow = hs + (size_t)tb * ld + kg * kq;
-        const float* wrow = Ws + (size_t)tr * ld + kg * kq;
-        for (int kk = 0; kk < kq; kk += 4) {
-          float4 hv[4], wv[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hv[i] = *reinterpret_cast<const float4*>(hrow + (size_t)(8 * i) * ld + kk);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) wv[j] = *reinterpret_cast<const float4*>(wrow + (size_t)(8 * j) * ld + kk);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc[i][j] = fmaf(hv[i].x, wv[j].x, acc[i][j]);
-              acc[i][j] = fmaf(hv[i].y, wv[j].y, acc[i][j]);
-              acc[i][j] = fmaf(hv[i].z, wv[j].z, acc[i][j]);
-              acc[i][j] = fmaf(hv[i].w, wv[j].w, acc[i][j]);
-            }
-        }
-        __syncthreads();  // everyone is done reading hs before it is reused as `part`
-      }
-      // partial sums -> part[kg][b][r]
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) part[((size_t)kg * kLstmBT + tb + 8 * i) * kLstmPartLd + tr + 8 * j] = acc[i][j];
-      __syncthreads();
-      float* hdst = hx + (size_t)(k & 1) * kLstmBT * Hp;
-#pragma unroll
-      for (int i = 0; i < kLstmPairs; ++i) {
-        if (pb[i] < 0) continue;
-        if (tt[i] >= 0) {
-          float pre[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int r = g * US + pu[i];
-            float s = xp[i][g];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s += part[((size_t)q * kLstmBT + pb[i]) * kLstmPartLd + r];
-            pre[g] = s;
+        float pre[4] = {xp[0], xp[1], xp[2], xp[3]};
+        if (k > 0) {
+          wait_flag(flag[i], (unsigned)(a.NSL * k));
+          const float* src = hx[i] + (size_t)((k - 1) & 1) * kLstmBT * Hp;
+          const int chunks = kLstmBT * (Hp / 4);
+          for (int c = tid; c < chunks; c += kLstmThreads) {
+            const int r = c / (Hp / 4), c4 = c - r * (Hp / 4);
+            cp_async16_cg(hs + (size_t)r * ld + c4 * 4, src + (size_t)r * Hp + c4 * 4);
           }
+          cp_async_wait_all();
+          __syncthreads();
+          // D[16 x 32 rows of this warp] += h[16 x kq] * W^T, 3xTF32
+          float acc[4][4], acl[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[j][q] = acl[j][q] = 0.f;
+          const float* hA = hs + kgrp * kq;
+          const float* wB = Ws + (size_t)(nh * 32) * ld + kgrp * kq;
+          for (int k0 = 0; k0 < kq; k0 += 8) {
+            uint32_t ah[4], al[4];
+            split2(hA[(size_t)g * ld + k0 + t], ah[0], al[0]);
+            split2(hA[(size_t)(g + 8) * ld + k0 + t], ah[1], al[1]);
+            split2(hA[(size_t)g * ld + k0 + t + 4], ah[2], al[2]);
+            split2(hA[(size_t)(g + 8) * ld + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t bh[2], bl[2];
+              split2(wB[(size_t)(j * 8 + g) * ld + k0 + t], bh[0], bl[0]);
+              split2(wB[(size_t)(j * 8 + g) * ld + k0 + t + 4], bh[1], bl[1]);
+              mma_tf32(acl[j], al, bh);
+              mma_tf32(acl[j], ah, bl);
+              mma_tf32(acc[j], ah, bh);
+            }
+          }
+          __syncthreads();  // everyone is done reading hs before it is reused for the partial sums
+          float* part = hs;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = nh * 32 + j * 8 + 2 * t;
+            *reinterpret_cast<float2*>(part + (size_t)(kgrp * kLstmBT + g) * kLstmPartLd + col) =
+                make_float2(acc[j][0] + acl[j][0], acc[j][1] + acl[j][1]);
+            *reinterpret_cast<float2*>(part + (size_t)(kgrp * kLstmBT + g + 8) * kLstmPartLd + col) =
+                make_float2(acc[j][2] + acl[j][2], acc[j][3] + acl[j][3]);
+          }
+          __syncthreads();
+          if (act) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int r = q * US + pu;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) pre[q] += part[(size_t)(kk * kLstmBT + pb) * kLstmPartLd + r];
+            }
+          }
+        }
+        float* hdst = hx[i] + (size_t)(k & 1) * kLstmBT * Hp;
+        if (act) {
           const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_(pre[3]);
           const float c = fmaf(fg, c_reg[i], ig * gg);
           const float h = og * tanhf(c);
           c_reg[i] = c;
           h_reg[i] = h;
-          const size_t tb_ = (size_t)tt[i] * a.B + b0 + pb[i];
-          a.out[(tb_ * 2 + dir) * H + u0 + pu[i]] = h;
+          const size_t tb_ = (size_t)tt * a.B + b0[i] + pb;
+          a.out[(tb_ * 2 + dir) * H + u0 + pu] = h;
           if (a.gates) {
-            float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu[i];
+            float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
             gp[0] = ig;
             gp[(size_t)H] = fg;
             gp[(size_t)2 * H] = gg;
             gp[(size_t)3 * H] = og;
           }
-          if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + pu[i]] = c;
+          if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + pu] = c;
         }
-        hdst[(size_t)pb[i] * Hp + u0 + pu[i]] = h_reg[i];  // finished samples keep publishing their last state
+        if (pok[i]) hdst[(size_t)pb * Hp + u0 + pu] = h_reg[i];  // finished samples keep publishing their last state
+        if (k + 1 < a.Tmax) signal_flag(flag[i]);
+        else __syncthreads();
       }
-      if (k + 1 < a.Tmax) signal_flag(flag);
-      else __syncthreads();
     }
   }
 }
@@ -227,63 +247,74 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
 __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a) {
   extern __shared__ __align__(16) float lstm_smem[];
   const int H = a.H, Hp = a.Hp, US = a.US, ld = Hp + 4;
-  float* Ws = lstm_smem;                   // [64][ld]
-  float* das = Ws + kLstmRows * ld;        // [32][68] gate gradients of this slice's units, row = sample
-  constexpr int ldd = kLstmRows + 4;
+  float* Ws = lstm_smem;                    // [64][ld]
+  float* dabuf = Ws + kLstmRows * ld;       // [NI][16][68] gate gradients of this slice's units, row = sample
   const int slice = blockIdx.x;
   const int u0 = slice * US;
   const int nu = min(US, H - u0);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
   const float* dout = a.xproj;  // [T,B,2H]
   float* dgates = a.out;        // [T,B,2,4H]
-  // partial-product mapping: thread -> samples tb+4i (i<8), columns tk*4 + 256*j .. +3
-  const int tb = tid & 3, tk = tid >> 2;
-  const int ncol4 = Hp / 4;  // float4 columns
+  const int pb = tid / US, pu = tid - pb * US;
+  const int ntiles = Hp / 8;    // 8-column tiles of the partial product; warp w owns tiles w, w+8, ...
 
-  for (int inst = blockIdx.y; inst < a.n_inst; inst += gridDim.y) {
-    const int dir = inst / a.NBT, bt = inst - dir * a.NBT;
-    const int b0 = bt * kLstmBT;
-    const int nb = min(kLstmBT, a.B - b0);
+  for (int grp = blockIdx.y; grp < a.n_groups; grp += gridDim.y) {
+    const int dir = grp / a.gpd, pair = grp - dir * a.gpd;
+    const int ni = min(kLstmNI, a.NBT - kLstmNI * pair);
     __syncthreads();
     load_w_slice(Ws, a.whh + (size_t)dir * 4 * H * H, H, Hp, US, u0, nu);
-    float* px = a.xchg + (size_t)inst * 2 * a.NSL * kLstmBT * Hp;
-    unsigned* flag = a.flags + inst;
-
-    int pb[kLstmPairs], pu[kLstmPairs], plen[kLstmPairs];
-    float dc_reg[kLstmPairs], dh_reg[kLstmPairs];
+    int b0[kLstmNI], plen[kLstmNI];
+    float* px[kLstmNI];
+    unsigned* flag[kLstmNI];
+    float dc_reg[kLstmNI], dh_reg[kLstmNI];
+    bool pok[kLstmNI];
+    unsigned round[kLstmNI];
 #pragma unroll
-    for (int i = 0; i < kLstmPairs; ++i) {
-      const int p = tid + i * kLstmThreads;
-      pb[i] = p / US;
-      pu[i] = p - pb[i] * US;
-      const bool ok = pb[i] < nb && pu[i] < nu && pb[i] < kLstmBT;
-      plen[i] = ok ? min(a.lens[b0 + pb[i]], a.Tmax) : 0;
-      if (!ok) pb[i] = -1;
+    for (int i = 0; i < kLstmNI; ++i) {
+      const int inst = dir * a.NBT + kLstmNI * pair + i;
+      b0[i] = (kLstmNI * pair + i) * kLstmBT;
+      const int nb = min(kLstmBT, a.B - b0[i]);
+      pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
+      plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
+      px[i] = a.xchg + (size_t)inst * 2 * a.NSL * kLstmBT * Hp;
+      flag[i] = a.flags + inst;
       dc_reg[i] = 0.f;
       dh_reg[i] = 0.f;
+      round[i] = 0;
     }
-    for (int i = tid; i < kLstmBT * ldd; i += kLstmThreads) das[i] = 0.f;
+    for (int i = tid; i < kLstmNI * kLstmBT * kLstmDaLd; i += kLstmThreads) dabuf[i] = 0.f;
     __syncthreads();
 
-    unsigned round = 0;
     for (int k = a.Tmax - 1; k >= 0; --k) {
-      // 1. gate gradients of this slice's units at step k
 #pragma unroll
-      for (int i = 0; i < kLstmPairs; ++i) {
-        if (pb[i] < 0) continue;
+      for (int i = 0; i < kLstmNI; ++i) {
+        if (i >= ni) continue;
+        float* das = dabuf + (size_t)i * kLstmBT * kLstmDaLd;
+        // 0. fold in the partial dh produced by the previous (later-in-time) step of this instance
+        if (k < a.Tmax - 1) {
+          wait_flag(flag[i], (unsigned)a.NSL * round[i]);
+          if (pok[i]) {
+            const float* psrc = px[i] + (size_t)((round[i] - 1) & 1) * a.NSL * kLstmBT * Hp;
+            float s = 0.f;
+            for (int sl = 0; sl < a.NSL; ++sl) s += __ldcg(psrc + ((size_t)sl * kLstmBT + pb) * Hp + u0 + pu);
+            dh_reg[i] += s;
+          }
+        }
+        // 1. gate gradients of this slice's units at step k
         float da[4] = {0.f, 0.f, 0.f, 0.f};
-        if (k < plen[i]) {
-          const int t = (dir == 0) ? k : plen[i] - 1 - k;
-          const size_t tb_ = (size_t)t * a.B + b0 + pb[i];
-          const float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu[i];
+        if (pok[i] && k < plen[i]) {
+          const int tq = (dir == 0) ? k : plen[i] - 1 - k;
+          const size_t tb_ = (size_t)tq * a.B + b0[i] + pb;
+          const float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
           const float ig = gp[0], fg = gp[(size_t)H], gg = gp[(size_t)2 * H], og = gp[(size_t)3 * H];
-          const float c = a.cst[(tb_ * 2 + dir) * H + u0 + pu[i]];
+          const float c = a.cst[(tb_ * 2 + dir) * H + u0 + pu];
           float c_prev = 0.f;
           if (k > 0) {
-            const int tp = (dir == 0) ? t - 1 : t + 1;
-            c_prev = a.cst[(((size_t)tp * a.B + b0 + pb[i]) * 2 + dir) * H + u0 + pu[i]];
+            const int tp = (dir == 0) ? tq - 1 : tq + 1;
+            c_prev = a.cst[(((size_t)tp * a.B + b0[i] + pb) * 2 + dir) * H + u0 + pu];
           }
-          const float dh = dout[(tb_ * 2 + dir) * H + u0 + pu[i]] + dh_reg[i];
+          const float dh = dout[(tb_ * 2 + dir) * H + u0 + pu] + dh_reg[i];
           const float tc = tanhf(c);
           const float dc = fmaf(dh * og, 1.f - tc * tc, dc_reg[i]);
           da[0] = dc * gg * ig * (1.f - ig);
@@ -291,69 +322,48 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
           da[2] = dc * ig * (1.f - gg * gg);
           da[3] = dh * tc * og * (1.f - og);
           dc_reg[i] = dc * fg;
-          float* dg = dgates + (tb_ * 2 + dir) * 4 * H + u0 + pu[i];
+          float* dg = dgates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
           dg[0] = da[0];
           dg[(size_t)H] = da[1];
           dg[(size_t)2 * H] = da[2];
           dg[(size_t)3 * H] = da[3];
-          dh_reg[i] = 0.f;  // replaced by the reduced partials below (stays 0 at k == 0)
+          dh_reg[i] = 0.f;  // consumed; the next reduce-scatter refills it
         }
+        if (k == 0) continue;
+        if (pok[i]) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) das[(size_t)pb[i] * ldd + g * US + pu[i]] = da[g];
-      }
-      if (k == 0) break;
-      __syncthreads();
-      // 2. partial dh_{k-1}[b, :] = das[b, 0:64] . Ws[0:64, :]   ->  px[round&1][slice][b][:]
-      float* pdst = px + ((size_t)(round & 1) * a.NSL + slice) * kLstmBT * Hp;
-      for (int cb = 0; cb < ncol4; cb += 128) {  // 128 float4 columns (= 2 per thread) per pass
-        float4 acc[8][2];
+          for (int q = 0; q < 4; ++q) das[(size_t)pb * kLstmDaLd + q * US + pu] = da[q];
+        }
+        __syncthreads();
+        // 2. partial dh_{k-1}[16, :] = das[16, 0:64] . Ws[0:64, :]  (tensor cores) -> px[round&1][slice]
+        float* pdst = px[i] + ((size_t)(round[i] & 1) * a.NSL + slice) * kLstmBT * Hp;
+        uint32_t ah[8][4], al[8][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int c0 = cb + tk, c1 = cb + tk + 64;
-        const bool v0 = c0 < ncol4, v1 = c1 < ncol4;
-        for (int r = 0; r < kLstmRows; r += 4) {
-          float4 dv[8];
+        for (int ks = 0; ks < 8; ++ks) {
+          split2(das[(size_t)g * kLstmDaLd + ks * 8 + t], ah[ks][0], al[ks][0]);
+          split2(das[(size_t)(g + 8) * kLstmDaLd + ks * 8 + t], ah[ks][1], al[ks][1]);
+          split2(das[(size_t)g * kLstmDaLd + ks * 8 + t + 4], ah[ks][2], al[ks][2]);
+          split2(das[(size_t)(g + 8) * kLstmDaLd + ks * 8 + t + 4], ah[ks][3], al[ks][3]);
+        }
+        for (int nt = warp; nt < ntiles; nt += 8) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* wB = Ws + nt * 8 + g;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dv[i] = *reinterpret_cast<const float4*>(das + (size_t)(tb + 4 * i) * ldd + r);
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const float4 w0 = v0 ? *reinterpret_cast<const float4*>(Ws + (size_t)(r + rr) * ld + c0 * 4)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 w1 = v1 ? *reinterpret_cast<const float4*>(Ws + (size_t)(r + rr) * ld + c1 * 4)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float d = (rr == 0) ? dv[i].x : (rr == 1) ? dv[i].y : (rr == 2) ? dv[i].z : dv[i].w;
-              acc[i][0].x = fmaf(d, w0.x, acc[i][0].x);
-              acc[i][0].y = fmaf(d, w0.y, acc[i][0].y);
-              acc[i][0].z = fmaf(d, w0.z, acc[i][0].z);
-              acc[i][0].w = fmaf(d, w0.w, acc[i][0].w);
-              acc[i][1].x = fmaf(d, w1.x, acc[i][1].x);
-              acc[i][1].y = fmaf(d, w1.y, acc[i][1].y);
-              acc[i][1].z = fmaf(d, w1.z, acc[i][1].z);
-              acc[i][1].w = fmaf(d, w1.w, acc[i][1].w);
-            }
+          for (int ks = 0; ks < 8; ++ks) {
+            uint32_t bh[2], bl[2];
+            split2(wB[(size_t)(ks * 8 + t) * ld], bh[0], bl[0]);
+            split2(wB[(size_t)(ks * 8 + t + 4) * ld], bh[1], bl[1]);
+            mma_tf32(acl, al[ks], bh);
+            mma_tf32(acl, ah[ks], bl);
+            mma_tf32(acc, ah[ks], bh);
           }
+          const int col = nt * 8 + 2 * t;
+          *reinterpret_cast<float2*>(pdst + (size_t)g * Hp + col) = make_float2(acc[0] + acl[0], acc[1] + acl[1]);
+          *reinterpret_cast<float2*>(pdst + (size_t)(g + 8) * Hp + col) = make_float2(acc[2] + acl[2], acc[3] + acl[3]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float* row = pdst + (size_t)(tb + 4 * i) * Hp;
-          if (v0) *reinterpret_cast<float4*>(row + c0 * 4) = acc[i][0];
-          if (v1) *reinterpret_cast<float4*>(row + c1 * 4) = acc[i][1];
-        }
-      }
-      // 3. meet the other slices, 4. reduce-scatter: own units <- sum over slices, fixed order
-      signal_flag(flag);
-      ++round;
-      wait_flag(flag, (unsigned)a.NSL * round);
-      const float* psrc = px + (size_t)((round - 1) & 1) * a.NSL * kLstmBT * Hp;
-#pragma unroll
-      for (int i = 0; i < kLstmPairs; ++i) {
-        if (pb[i] < 0) continue;
-        float s = 0.f;
-        for (int sl = 0; sl < a.NSL; ++sl)
-          s += __ldcg(psrc + ((size_t)sl * kLstmBT + pb[i]) * Hp + u0 + pu[i]);
-        dh_reg[i] += s;
+        // 3. publish; the reduce-scatter happens at the top of this instance's next step
+        signal_flag(flag[i]);
+        ++round[i];
       }
     }
   }
@@ -367,13 +377,19 @@ static int lstm_geometry(int B, int H, LstmArgs* a, size_t* smem, int* grid_y, b
   if (H < 1 || H > 32 * kLstmMaxUS) return VOCR_INVALID_VALUE;
   a->US = ceil_div(H, 32);
   a->NSL = ceil_div(H, a->US);
-  a->Hp = ceil_div(H, 16) * 16;
+  a->Hp = ceil_div(H, 32) * 32;
   a->NBT = ceil_div(B, kLstmBT);
-  a->n_inst = 2 * a->NBT;
+  a->gpd = ceil_div(a->NBT, kLstmNI);
+  a->n_groups = 2 * a->gpd;
   const size_t ld = a->Hp + 4;
-  *smem = sizeof(float) * (kLstmRows * ld + (bwd ? kLstmBT * (kLstmRows + 4) : max((size_t)kLstmBT * ld, (size_t)4 * kLstmBT * kLstmPartLd)));
-  *grid_y = max(1, min(a->n_inst, kNumSMs / a->NSL));
+  *smem = sizeof(float) * (kLstmRows * ld + (bwd ? (size_t)kLstmNI * kLstmBT * kLstmDaLd
+                                                  : (size_t)kLstmNI * lstm_hs_floats(a->Hp)));
+  *grid_y = max(1, min(a->n_groups, kNumSMs / a->NSL));
   return VOCR_OK;
+}
+
+static size_t lstm_xchg_bytes(const LstmArgs& a, bool bwd) {
+  return sizeof(float) * (size_t)(2 * a.NBT) * 2 * kLstmBT * a.Hp * (bwd ? a.NSL : 1);
 }
 
 extern "C" size_t vocr_bilstm_workspace_size(int B, int H, int backward) {
@@ -381,8 +397,7 @@ extern "C" size_t vocr_bilstm_workspace_size(int B, int H, int backward) {
   size_t smem;
   int gy;
   if (lstm_geometry(B, H, &a, &smem, &gy, backward != 0) != VOCR_OK) return 0;
-  const size_t xchg = sizeof(float) * (size_t)a.n_inst * 2 * kLstmBT * a.Hp * (backward ? a.NSL : 1);
-  return 256 + ((sizeof(unsigned) * a.n_inst + 255) & ~size_t(255)) + xchg;
+  return 256 + ((sizeof(unsigned) * 2 * a.NBT + 255) & ~size_t(255)) + lstm_xchg_bytes(a, backward != 0);
 }
 
 static int lstm_launch(bool bwd, LstmArgs a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -391,8 +406,8 @@ static int lstm_launch(bool bwd, LstmArgs a, void* workspace, size_t workspace_b
   int st = lstm_geometry(a.B, a.H, &a, &smem, &gy, bwd);
   if (st != VOCR_OK) return st;
   uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
-  const size_t flag_bytes = (sizeof(unsigned) * a.n_inst + 255) & ~size_t(255);
-  const size_t xchg = sizeof(float) * (size_t)a.n_inst * 2 * kLstmBT * a.Hp * (bwd ? a.NSL : 1);
+  const size_t flag_bytes = (sizeof(unsigned) * 2 * a.NBT + 255) & ~size_t(255);
+  const size_t xchg = lstm_xchg_bytes(a, bwd);
   if ((w - reinterpret_cast<uintptr_t>(workspace)) + flag_bytes + xchg > workspace_bytes) return VOCR_INVALID_VALUE;
   a.flags = reinterpret_cast<unsigned*>(w);
   a.xchg = reinterpret_cast<float*>(w + flag_bytes);
