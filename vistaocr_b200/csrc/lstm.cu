@@ -27,7 +27,7 @@
 
 namespace vocr {
 
-constexpr int kLstmThreads = 256;
+constexpr int kLstmThreads = 320;     // 8 compute warps + one communication warp per interleaved instance
 constexpr int kLstmBT = 16;        // samples per instance = MMA M
 constexpr int kLstmNI = 2;         // instances interleaved per CTA
 constexpr int kLstmMaxUS = 16;     // hidden units per slice
@@ -107,137 +107,205 @@ __host__ __device__ inline int lstm_hs_floats(int Hp) {
   return a > b ? a : b;
 }
 
+// named barrier among the 256 compute threads only (the producer warps never join it)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival per warp, after the warp's lanes have synchronised (orders every lane's prior writes before the arrive)
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive1(bar);
+}
+__device__ __forceinline__ void poll_flag(const unsigned* flag, unsigned target) {
+  unsigned spins = 0;
+  while (ld_acquire(flag) < target) {
+    if (++spins > (1u << 26)) asm volatile("trap;");  // ~seconds: a lost peer must not hang the box
+  }
+}
+
+// Warp roles: warps 0-7 compute; warp 8+i is the COMMUNICATION warp of instance i.  It waits for the instance's flag,
+// pulls the 16 x H tile of h_{t-1} into shared memory with bulk async copies (mbarrier `full`), and - once the compute
+// warps have published their piece of h_t (mbarrier `written`) - makes it visible (fence) and bumps the flag.  The
+// compute warps therefore never sit on an L2 round trip: while instance 0's exchange is in flight they work on
+// instance 1.
+
 // ================================================ forward =====================================================
 __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a) {
   extern __shared__ __align__(16) float lstm_smem[];
   const int H = a.H, Hp = a.Hp, US = a.US, ld = Hp + 4;
-  float* Ws = lstm_smem;                          // [64][ld]
-  float* hbuf = Ws + kLstmRows * ld;              // [NI][hs_floats]: h tile, later aliased by the K-split partials
-  const int hs_floats = lstm_hs_floats(Hp);
+  float* Ws = lstm_smem;                                   // [64][ld]
+  float* hbuf = Ws + kLstmRows * ld;                       // [NI][16][ld]
+  float* part = hbuf + (size_t)kLstmNI * kLstmBT * ld;     // [4][16][72]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 4 * kLstmBT * kLstmPartLd);
+  uint64_t* full = bars;                  // [NI] h tile landed           (tx bytes)
+  uint64_t* empty = bars + kLstmNI;       // [NI] product done with hs[i]  (8 warp arrivals)
+  uint64_t* written = bars + 2 * kLstmNI; // [NI] h_t piece stored         (8 warp arrivals)
   const int slice = blockIdx.x;
   const int u0 = slice * US;
   const int nu = min(US, H - u0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;          // mma fragment coordinates
-  const int kgrp = warp >> 1, nh = warp & 1;      // K quarter, half of the 64 gate rows
-  const int kq = Hp / 4;                          // K range of a quarter (Hp % 32 == 0 -> multiple of 8)
-  // gate epilogue: one (sample, unit) pair per thread and instance
-  const int pb = tid / US, pu = tid - pb * US;
+  if (tid == 0) {
+    for (int i = 0; i < kLstmNI; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 8);
+      mbar_init(&written[i], 8);
+    }
+    mbar_fence_init();
+  }
+  // running phase counters (barriers are used across groups without re-initialisation)
+  unsigned n_full[kLstmNI] = {0, 0}, n_empty[kLstmNI] = {0, 0}, n_written[kLstmNI] = {0, 0};
 
   for (int grp = blockIdx.y; grp < a.n_groups; grp += gridDim.y) {
     const int dir = grp / a.gpd, pair = grp - dir * a.gpd;
     const int ni = min(kLstmNI, a.NBT - kLstmNI * pair);
     __syncthreads();
     load_w_slice(Ws, a.whh + (size_t)dir * 4 * H * H, H, Hp, US, u0, nu);
-    int b0[kLstmNI], plen[kLstmNI];
-    float* hx[kLstmNI];
-    unsigned* flag[kLstmNI];
-    float c_reg[kLstmNI], h_reg[kLstmNI];
-    bool pok[kLstmNI];
-#pragma unroll
-    for (int i = 0; i < kLstmNI; ++i) {
-      const int inst = dir * a.NBT + kLstmNI * pair + i;
-      b0[i] = (kLstmNI * pair + i) * kLstmBT;
-      const int nb = min(kLstmBT, a.B - b0[i]);
-      pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
-      plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
-      hx[i] = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
-      flag[i] = a.flags + inst;
-      c_reg[i] = 0.f;
-      h_reg[i] = 0.f;
-    }
+    for (int i = tid; i < kLstmNI * kLstmBT * ld; i += kLstmThreads) hbuf[i] = 0.f;  // padding columns stay zero
     __syncthreads();
 
-    for (int k = 0; k < a.Tmax; ++k) {
+    if (warp >= 8) {
+      // ------------------------------ communication warp of instance i ------------------------------
+      const int i = warp - 8;
+      if (i < ni) {
+        const int inst = dir * a.NBT + kLstmNI * pair + i;
+        float* hx = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
+        unsigned* flag = a.flags + inst;
+        float* hs = hbuf + (size_t)i * kLstmBT * ld;
+        for (int k = 0; k < a.Tmax; ++k) {
+          if (k > 0) {
+            if (k > 1) {  // hs[i] is free once the product of step k-1 has consumed it
+              mbar_wait_or_trap(&empty[i], (n_empty[i] & 1u));
+              ++n_empty[i];
+            }
+            if (lane == 0) {
+              poll_flag(flag, (unsigned)(a.NSL * k));
+              asm volatile("fence.proxy.async;" ::: "memory");
+              mbar_arrive_expect_tx(&full[i], (uint32_t)(kLstmBT * Hp * 4));
+            }
+            __syncwarp();
+            if (lane < kLstmBT) {
+              asm volatile("fence.proxy.async;" ::: "memory");
+              bulk_g2s(hs + (size_t)lane * ld, hx + (size_t)((k - 1) & 1) * kLstmBT * Hp + (size_t)lane * Hp,
+                       (uint32_t)(Hp * 4), &full[i]);
+            }
+          }
+          if (k + 1 < a.Tmax) {
+            mbar_wait_or_trap(&written[i], (n_written[i] & 1u));
+            ++n_written[i];
+            if (lane == 0) {
+              __threadfence();
+              red_release(flag);
+            }
+          }
+        }
+        if (a.Tmax > 1) {  // drain: the last product's release of hs[i] (keeps the phase counters in step)
+          mbar_wait_or_trap(&empty[i], (n_empty[i] & 1u));
+          ++n_empty[i];
+        }
+      }
+    } else {
+      // ------------------------------------- compute warps -------------------------------------
+      const int g = lane >> 2, t = lane & 3;          // mma fragment coordinates
+      const int kgrp = warp >> 1, nh = warp & 1;      // K quarter, half of the 64 gate rows
+      const int kq = Hp / 4;                          // K range of a quarter (Hp % 32 == 0 -> multiple of 8)
+      const int pb = tid / US, pu = tid - pb * US;    // gate epilogue: one (sample, unit) pair per thread, instance
+      int b0[kLstmNI], plen[kLstmNI];
+      float* hx[kLstmNI];
+      float c_reg[kLstmNI], h_reg[kLstmNI];
+      bool pok[kLstmNI];
 #pragma unroll
       for (int i = 0; i < kLstmNI; ++i) {
-        if (i >= ni) continue;
-        float* hs = hbuf + (size_t)i * hs_floats;
-        // this step's input projections (independent of the recurrence): issue the loads before the wait
-        const bool act = pok[i] && k < plen[i];
-        const int tt = act ? (dir == 0 ? k : plen[i] - 1 - k) : -1;
-        float xp[4] = {0.f, 0.f, 0.f, 0.f};
-        if (act) {
-          const float* xr = a.xproj + (((size_t)tt * a.B + b0[i] + pb) * 2 + dir) * 4 * H + u0 + pu;
+        const int inst = dir * a.NBT + kLstmNI * pair + i;
+        b0[i] = (kLstmNI * pair + i) * kLstmBT;
+        const int nb = min(kLstmBT, a.B - b0[i]);
+        pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
+        plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
+        hx[i] = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
+        c_reg[i] = 0.f;
+        h_reg[i] = 0.f;
+      }
+      for (int k = 0; k < a.Tmax; ++k) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xp[q] = __ldg(xr + (size_t)q * H);
-        }
-        float pre[4] = {xp[0], xp[1], xp[2], xp[3]};
-        if (k > 0) {
-          wait_flag(flag[i], (unsigned)(a.NSL * k));
-          const float* src = hx[i] + (size_t)((k - 1) & 1) * kLstmBT * Hp;
-          const int chunks = kLstmBT * (Hp / 4);
-          for (int c = tid; c < chunks; c += kLstmThreads) {
-            const int r = c / (Hp / 4), c4 = c - r * (Hp / 4);
-            cp_async16_cg(hs + (size_t)r * ld + c4 * 4, src + (size_t)r * Hp + c4 * 4);
+        for (int i = 0; i < kLstmNI; ++i) {
+          if (i >= ni) continue;
+          const float* hs = hbuf + (size_t)i * kLstmBT * ld;
+          const bool act = pok[i] && k < plen[i];
+          const int tt = act ? (dir == 0 ? k : plen[i] - 1 - k) : -1;
+          float pre[4] = {0.f, 0.f, 0.f, 0.f};
+          if (act) {  // input projections: independent of the recurrence, loads issued before any wait
+            const float* xr = a.xproj + (((size_t)tt * a.B + b0[i] + pb) * 2 + dir) * 4 * H + u0 + pu;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pre[q] = __ldg(xr + (size_t)q * H);
           }
-          cp_async_wait_all();
-          __syncthreads();
-          // D[16 x 32 rows of this warp] += h[16 x kq] * W^T, 3xTF32
-          float acc[4][4], acl[4][4];
+          if (k > 0) {
+            mbar_wait_or_trap(&full[i], (n_full[i] & 1u));
+            ++n_full[i];
+            // D[16 x 32 rows of this warp] += h[16 x kq] * W^T, 3xTF32
+            float acc[4][4], acl[4][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[j][q] = acl[j][q] = 0.f;
-          const float* hA = hs + kgrp * kq;
-          const float* wB = Ws + (size_t)(nh * 32) * ld + kgrp * kq;
-          for (int k0 = 0; k0 < kq; k0 += 8) {
-            uint32_t ah[4], al[4];
-            split2(hA[(size_t)g * ld + k0 + t], ah[0], al[0]);
-            split2(hA[(size_t)(g + 8) * ld + k0 + t], ah[1], al[1]);
-            split2(hA[(size_t)g * ld + k0 + t + 4], ah[2], al[2]);
-            split2(hA[(size_t)(g + 8) * ld + k0 + t + 4], ah[3], al[3]);
+              for (int q = 0; q < 4; ++q) acc[j][q] = acl[j][q] = 0.f;
+            const float* hA = hs + kgrp * kq;
+            const float* wB = Ws + (size_t)(nh * 32) * ld + kgrp * kq;
+            for (int k0 = 0; k0 < kq; k0 += 8) {
+              uint32_t ah[4], al[4];
+              split2(hA[(size_t)g * ld + k0 + t], ah[0], al[0]);
+              split2(hA[(size_t)(g + 8) * ld + k0 + t], ah[1], al[1]);
+              split2(hA[(size_t)g * ld + k0 + t + 4], ah[2], al[2]);
+              split2(hA[(size_t)(g + 8) * ld + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t bh[2], bl[2];
+                split2(wB[(size_t)(j * 8 + g) * ld + k0 + t], bh[0], bl[0]);
+                split2(wB[(size_t)(j * 8 + g) * ld + k0 + t + 4], bh[1], bl[1]);
+                mma_tf32(acl[j], al, bh);
+                mma_tf32(acl[j], ah, bl);
+                mma_tf32(acc[j], ah, bh);
+              }
+            }
+            warp_arrive(&empty[i]);  // hs[i] may be refilled
+            compute_sync();          // the previous instance-step's readers of `part` are done
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint32_t bh[2], bl[2];
-              split2(wB[(size_t)(j * 8 + g) * ld + k0 + t], bh[0], bl[0]);
-              split2(wB[(size_t)(j * 8 + g) * ld + k0 + t + 4], bh[1], bl[1]);
-              mma_tf32(acl[j], al, bh);
-              mma_tf32(acl[j], ah, bl);
-              mma_tf32(acc[j], ah, bh);
+              const int col = nh * 32 + j * 8 + 2 * t;
+              *reinterpret_cast<float2*>(part + (size_t)(kgrp * kLstmBT + g) * kLstmPartLd + col) =
+                  make_float2(acc[j][0] + acl[j][0], acc[j][1] + acl[j][1]);
+              *reinterpret_cast<float2*>(part + (size_t)(kgrp * kLstmBT + g + 8) * kLstmPartLd + col) =
+                  make_float2(acc[j][2] + acl[j][2], acc[j][3] + acl[j][3]);
+            }
+            compute_sync();
+            if (act) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int r = q * US + pu;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) pre[q] += part[(size_t)(kk * kLstmBT + pb) * kLstmPartLd + r];
+              }
             }
           }
-          __syncthreads();  // everyone is done reading hs before it is reused for the partial sums
-          float* part = hs;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = nh * 32 + j * 8 + 2 * t;
-            *reinterpret_cast<float2*>(part + (size_t)(kgrp * kLstmBT + g) * kLstmPartLd + col) =
-                make_float2(acc[j][0] + acl[j][0], acc[j][1] + acl[j][1]);
-            *reinterpret_cast<float2*>(part + (size_t)(kgrp * kLstmBT + g + 8) * kLstmPartLd + col) =
-                make_float2(acc[j][2] + acl[j][2], acc[j][3] + acl[j][3]);
-          }
-          __syncthreads();
           if (act) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int r = q * US + pu;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) pre[q] += part[(size_t)(kk * kLstmBT + pb) * kLstmPartLd + r];
+            const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_(pre[3]);
+            const float c = fmaf(fg, c_reg[i], ig * gg);
+            const float h = og * tanhf(c);
+            c_reg[i] = c;
+            h_reg[i] = h;
+            const size_t tb_ = (size_t)tt * a.B + b0[i] + pb;
+            a.out[(tb_ * 2 + dir) * H + u0 + pu] = h;
+            if (a.gates) {
+              float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
+              gp[0] = ig;
+              gp[(size_t)H] = fg;
+              gp[(size_t)2 * H] = gg;
+              gp[(size_t)3 * H] = og;
             }
+            if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + pu] = c;
           }
+          // finished samples keep publishing their last state
+          if (pok[i]) hx[i][(size_t)(k & 1) * kLstmBT * Hp + (size_t)pb * Hp + u0 + pu] = h_reg[i];
+          if (k + 1 < a.Tmax) warp_arrive(&written[i]);
         }
-        float* hdst = hx[i] + (size_t)(k & 1) * kLstmBT * Hp;
-        if (act) {
-          const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_(pre[3]);
-          const float c = fmaf(fg, c_reg[i], ig * gg);
-          const float h = og * tanhf(c);
-          c_reg[i] = c;
-          h_reg[i] = h;
-          const size_t tb_ = (size_t)tt * a.B + b0[i] + pb;
-          a.out[(tb_ * 2 + dir) * H + u0 + pu] = h;
-          if (a.gates) {
-            float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
-            gp[0] = ig;
-            gp[(size_t)H] = fg;
-            gp[(size_t)2 * H] = gg;
-            gp[(size_t)3 * H] = og;
-          }
-          if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + pu] = c;
-        }
-        if (pok[i]) hdst[(size_t)pb * Hp + u0 + pu] = h_reg[i];  // finished samples keep publishing their last state
-        if (k + 1 < a.Tmax) signal_flag(flag[i]);
-        else __syncthreads();
       }
     }
   }
@@ -249,121 +317,161 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
   const int H = a.H, Hp = a.Hp, US = a.US, ld = Hp + 4;
   float* Ws = lstm_smem;                    // [64][ld]
   float* dabuf = Ws + kLstmRows * ld;       // [NI][16][68] gate gradients of this slice's units, row = sample
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dabuf + kLstmNI * kLstmBT * kLstmDaLd);
+  uint64_t* ready = bars;                   // [NI] all slices published their partial dh  (1 arrival, comm warp)
+  uint64_t* written = bars + kLstmNI;       // [NI] this slice's partial stored            (8 warp arrivals)
   const int slice = blockIdx.x;
   const int u0 = slice * US;
   const int nu = min(US, H - u0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
   const float* dout = a.xproj;  // [T,B,2H]
   float* dgates = a.out;        // [T,B,2,4H]
-  const int pb = tid / US, pu = tid - pb * US;
-  const int ntiles = Hp / 8;    // 8-column tiles of the partial product; warp w owns tiles w, w+8, ...
+  if (tid == 0) {
+    for (int i = 0; i < kLstmNI; ++i) {
+      mbar_init(&ready[i], 1);
+      mbar_init(&written[i], 8);
+    }
+    mbar_fence_init();
+  }
+  unsigned n_ready[kLstmNI] = {0, 0}, n_written[kLstmNI] = {0, 0};
 
   for (int grp = blockIdx.y; grp < a.n_groups; grp += gridDim.y) {
     const int dir = grp / a.gpd, pair = grp - dir * a.gpd;
     const int ni = min(kLstmNI, a.NBT - kLstmNI * pair);
     __syncthreads();
     load_w_slice(Ws, a.whh + (size_t)dir * 4 * H * H, H, Hp, US, u0, nu);
-    int b0[kLstmNI], plen[kLstmNI];
-    float* px[kLstmNI];
-    unsigned* flag[kLstmNI];
-    float dc_reg[kLstmNI], dh_reg[kLstmNI];
-    bool pok[kLstmNI];
-    unsigned round[kLstmNI];
-#pragma unroll
-    for (int i = 0; i < kLstmNI; ++i) {
-      const int inst = dir * a.NBT + kLstmNI * pair + i;
-      b0[i] = (kLstmNI * pair + i) * kLstmBT;
-      const int nb = min(kLstmBT, a.B - b0[i]);
-      pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
-      plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
-      px[i] = a.xchg + (size_t)inst * 2 * a.NSL * kLstmBT * Hp;
-      flag[i] = a.flags + inst;
-      dc_reg[i] = 0.f;
-      dh_reg[i] = 0.f;
-      round[i] = 0;
-    }
     for (int i = tid; i < kLstmNI * kLstmBT * kLstmDaLd; i += kLstmThreads) dabuf[i] = 0.f;
     __syncthreads();
 
-    for (int k = a.Tmax - 1; k >= 0; --k) {
+    if (warp >= 8) {
+      // ------------------------------ communication warp of instance i ------------------------------
+      const int i = warp - 8;
+      if (i < ni) {
+        unsigned* flag = a.flags + dir * a.NBT + kLstmNI * pair + i;
+        unsigned round = 0;
+        for (int k = a.Tmax - 1; k >= 1; --k) {
+          mbar_wait_or_trap(&written[i], (n_written[i] & 1u));
+          ++n_written[i];
+          if (lane == 0) {
+            __threadfence();
+            red_release(flag);
+            ++round;
+            poll_flag(flag, (unsigned)a.NSL * round);
+            mbar_arrive1(&ready[i]);
+          }
+          round = __shfl_sync(0xffffffffu, round, 0);
+        }
+      }
+    } else {
+      // ------------------------------------- compute warps -------------------------------------
+      const int g = lane >> 2, t = lane & 3;
+      const int pb = tid / US, pu = tid - pb * US;
+      const int ntiles = Hp / 8;  // 8-column tiles of the partial product; warp w owns tiles w, w+8, ...
+      int b0[kLstmNI], plen[kLstmNI];
+      float* px[kLstmNI];
+      float dc_reg[kLstmNI], dh_reg[kLstmNI];
+      bool pok[kLstmNI];
+      unsigned round[kLstmNI];
 #pragma unroll
       for (int i = 0; i < kLstmNI; ++i) {
-        if (i >= ni) continue;
-        float* das = dabuf + (size_t)i * kLstmBT * kLstmDaLd;
-        // 0. fold in the partial dh produced by the previous (later-in-time) step of this instance
-        if (k < a.Tmax - 1) {
-          wait_flag(flag[i], (unsigned)a.NSL * round[i]);
+        const int inst = dir * a.NBT + kLstmNI * pair + i;
+        b0[i] = (kLstmNI * pair + i) * kLstmBT;
+        const int nb = min(kLstmBT, a.B - b0[i]);
+        pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
+        plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
+        px[i] = a.xchg + (size_t)inst * 2 * a.NSL * kLstmBT * Hp;
+        dc_reg[i] = 0.f;
+        dh_reg[i] = 0.f;
+        round[i] = 0;
+      }
+      for (int k = a.Tmax - 1; k >= 0; --k) {
+#pragma unroll
+        for (int i = 0; i < kLstmNI; ++i) {
+          if (i >= ni) continue;
+          float* das = dabuf + (size_t)i * kLstmBT * kLstmDaLd;
+          // saved activations of this step: independent of the recurrence, loads issued before the wait
+          const bool act = pok[i] && k < plen[i];
+          float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, c = 0.f, c_prev = 0.f, dy = 0.f;
+          size_t tb_ = 0;
+          if (act) {
+            const int tq = (dir == 0) ? k : plen[i] - 1 - k;
+            tb_ = (size_t)tq * a.B + b0[i] + pb;
+            const float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
+            ig = gp[0]; fg = gp[(size_t)H]; gg = gp[(size_t)2 * H]; og = gp[(size_t)3 * H];
+            c = a.cst[(tb_ * 2 + dir) * H + u0 + pu];
+            if (k > 0) {
+              const int tp = (dir == 0) ? tq - 1 : tq + 1;
+              c_prev = a.cst[(((size_t)tp * a.B + b0[i] + pb) * 2 + dir) * H + u0 + pu];
+            }
+            dy = dout[(tb_ * 2 + dir) * H + u0 + pu];
+          }
+          // 0. fold in the partial dh produced by the previous (later-in-time) step of this instance
+          if (k < a.Tmax - 1) {
+            mbar_wait_or_trap(&ready[i], (n_ready[i] & 1u));
+            ++n_ready[i];
+            if (pok[i]) {
+              const float* psrc = px[i] + (size_t)((round[i] - 1) & 1) * a.NSL * kLstmBT * Hp;
+              float s = 0.f;
+              for (int sl = 0; sl < a.NSL; ++sl) s += __ldcg(psrc + ((size_t)sl * kLstmBT + pb) * Hp + u0 + pu);
+              dh_reg[i] += s;
+            }
+          }
+          // 1. gate gradients of this slice's units at step k
+          float da[4] = {0.f, 0.f, 0.f, 0.f};
+          if (act) {
+            const float dh = dy + dh_reg[i];
+            const float tc = tanhf(c);
+            const float dc = fmaf(dh * og, 1.f - tc * tc, dc_reg[i]);
+            da[0] = dc * gg * ig * (1.f - ig);
+            da[1] = dc * c_prev * fg * (1.f - fg);
+            da[2] = dc * ig * (1.f - gg * gg);
+            da[3] = dh * tc * og * (1.f - og);
+            dc_reg[i] = dc * fg;
+            float* dg = dgates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
+            dg[0] = da[0];
+            dg[(size_t)H] = da[1];
+            dg[(size_t)2 * H] = da[2];
+            dg[(size_t)3 * H] = da[3];
+            dh_reg[i] = 0.f;  // consumed; the next reduce-scatter refills it
+          }
+          if (k == 0) continue;
           if (pok[i]) {
-            const float* psrc = px[i] + (size_t)((round[i] - 1) & 1) * a.NSL * kLstmBT * Hp;
-            float s = 0.f;
-            for (int sl = 0; sl < a.NSL; ++sl) s += __ldcg(psrc + ((size_t)sl * kLstmBT + pb) * Hp + u0 + pu);
-            dh_reg[i] += s;
-          }
-        }
-        // 1. gate gradients of this slice's units at step k
-        float da[4] = {0.f, 0.f, 0.f, 0.f};
-        if (pok[i] && k < plen[i]) {
-          const int tq = (dir == 0) ? k : plen[i] - 1 - k;
-          const size_t tb_ = (size_t)tq * a.B + b0[i] + pb;
-          const float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
-          const float ig = gp[0], fg = gp[(size_t)H], gg = gp[(size_t)2 * H], og = gp[(size_t)3 * H];
-          const float c = a.cst[(tb_ * 2 + dir) * H + u0 + pu];
-          float c_prev = 0.f;
-          if (k > 0) {
-            const int tp = (dir == 0) ? tq - 1 : tq + 1;
-            c_prev = a.cst[(((size_t)tp * a.B + b0[i] + pb) * 2 + dir) * H + u0 + pu];
-          }
-          const float dh = dout[(tb_ * 2 + dir) * H + u0 + pu] + dh_reg[i];
-          const float tc = tanhf(c);
-          const float dc = fmaf(dh * og, 1.f - tc * tc, dc_reg[i]);
-          da[0] = dc * gg * ig * (1.f - ig);
-          da[1] = dc * c_prev * fg * (1.f - fg);
-          da[2] = dc * ig * (1.f - gg * gg);
-          da[3] = dh * tc * og * (1.f - og);
-          dc_reg[i] = dc * fg;
-          float* dg = dgates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
-          dg[0] = da[0];
-          dg[(size_t)H] = da[1];
-          dg[(size_t)2 * H] = da[2];
-          dg[(size_t)3 * H] = da[3];
-          dh_reg[i] = 0.f;  // consumed; the next reduce-scatter refills it
-        }
-        if (k == 0) continue;
-        if (pok[i]) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) das[(size_t)pb * kLstmDaLd + q * US + pu] = da[q];
-        }
-        __syncthreads();
-        // 2. partial dh_{k-1}[16, :] = das[16, 0:64] . Ws[0:64, :]  (tensor cores) -> px[round&1][slice]
-        float* pdst = px[i] + ((size_t)(round[i] & 1) * a.NSL + slice) * kLstmBT * Hp;
-        uint32_t ah[8][4], al[8][4];
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          split2(das[(size_t)g * kLstmDaLd + ks * 8 + t], ah[ks][0], al[ks][0]);
-          split2(das[(size_t)(g + 8) * kLstmDaLd + ks * 8 + t], ah[ks][1], al[ks][1]);
-          split2(das[(size_t)g * kLstmDaLd + ks * 8 + t + 4], ah[ks][2], al[ks][2]);
-          split2(das[(size_t)(g + 8) * kLstmDaLd + ks * 8 + t + 4], ah[ks][3], al[ks][3]);
-        }
-        for (int nt = warp; nt < ntiles; nt += 8) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* wB = Ws + nt * 8 + g;
+            for (int q = 0; q < 4; ++q) das[(size_t)pb * kLstmDaLd + q * US + pu] = da[q];
+          }
+          compute_sync();
+          // 2. partial dh_{k-1}[16, :] = das[16, 0:64] . Ws[0:64, :]  (tensor cores) -> px[round&1][slice]
+          float* pdst = px[i] + ((size_t)(round[i] & 1) * a.NSL + slice) * kLstmBT * Hp;
+          uint32_t ah[8][4], al[8][4];
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            uint32_t bh[2], bl[2];
-            split2(wB[(size_t)(ks * 8 + t) * ld], bh[0], bl[0]);
-            split2(wB[(size_t)(ks * 8 + t + 4) * ld], bh[1], bl[1]);
-            mma_tf32(acl, al[ks], bh);
-            mma_tf32(acl, ah[ks], bl);
-            mma_tf32(acc, ah[ks], bh);
+            split2(das[(size_t)g * kLstmDaLd + ks * 8 + t], ah[ks][0], al[ks][0]);
+            split2(das[(size_t)(g + 8) * kLstmDaLd + ks * 8 + t], ah[ks][1], al[ks][1]);
+            split2(das[(size_t)g * kLstmDaLd + ks * 8 + t + 4], ah[ks][2], al[ks][2]);
+            split2(das[(size_t)(g + 8) * kLstmDaLd + ks * 8 + t + 4], ah[ks][3], al[ks][3]);
           }
-          const int col = nt * 8 + 2 * t;
-          *reinterpret_cast<float2*>(pdst + (size_t)g * Hp + col) = make_float2(acc[0] + acl[0], acc[1] + acl[1]);
-          *reinterpret_cast<float2*>(pdst + (size_t)(g + 8) * Hp + col) = make_float2(acc[2] + acl[2], acc[3] + acl[3]);
+          compute_sync();  // das[i] may be rewritten by the next step of this instance
+          for (int nt = warp; nt < ntiles; nt += 8) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* wB = Ws + nt * 8 + g;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              uint32_t bh[2], bl[2];
+              split2(wB[(size_t)(ks * 8 + t) * ld], bh[0], bl[0]);
+              split2(wB[(size_t)(ks * 8 + t + 4) * ld], bh[1], bl[1]);
+              mma_tf32(acl, al[ks], bh);
+              mma_tf32(acl, ah[ks], bl);
+              mma_tf32(acc, ah[ks], bh);
+            }
+            const int col = nt * 8 + 2 * t;
+            *reinterpret_cast<float2*>(pdst + (size_t)g * Hp + col) = make_float2(acc[0] + acl[0], acc[1] + acl[1]);
+            *reinterpret_cast<float2*>(pdst + (size_t)(g + 8) * Hp + col) =
+                make_float2(acc[2] + acl[2], acc[3] + acl[3]);
+          }
+          // 3. publish through the communication warp; the reduce-scatter happens at the top of the next step
+          warp_arrive(&written[i]);
+          ++round[i];
         }
-        // 3. publish; the reduce-scatter happens at the top of this instance's next step
-        signal_flag(flag[i]);
-        ++round[i];
       }
     }
   }
@@ -383,7 +491,7 @@ static int lstm_geometry(int B, int H, LstmArgs* a, size_t* smem, int* grid_y, b
   a->n_groups = 2 * a->gpd;
   const size_t ld = a->Hp + 4;
   *smem = sizeof(float) * (kLstmRows * ld + (bwd ? (size_t)kLstmNI * kLstmBT * kLstmDaLd
-                                                  : (size_t)kLstmNI * lstm_hs_floats(a->Hp)));
+                                                  : (size_t)kLstmNI * kLstmBT * ld + 4 * kLstmBT * kLstmPartLd)) + 64;
   *grid_y = max(1, min(a->n_groups, kNumSMs / a->NSL));
   return VOCR_OK;
 }
