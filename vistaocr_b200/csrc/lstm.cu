@@ -78,8 +78,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- tensor-core helpers: m16n8k8 TF32, operands split hi/lo in registers (3xTF32) ---------------------------------
+// hi = x with the 13 low mantissa bits cleared (exactly a TF32 value; one LOP3), lo = x - hi (exact; one FADD).
+// cvt.rna.tf32 would halve |lo| but expands to ~6 instructions here, and this split runs 12x per k-step on the
+// critical path; with truncation the dropped lo*lo term is still only 2^-20 relative.
 __device__ __forceinline__ void split2(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));  // the tensor core ignores the 13 low mantissa bits of lo
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
               for (int q = 0; q < 4; ++q) acc[j][q] = acl[j][q] = 0.f;
             const float* hA = hs + kgrp * kq;
             const float* wB = Ws + (size_t)(nh * 32) * ld + kgrp * kq;
+#pragma unroll 4
             for (int k0 = 0; k0 < kq; k0 += 8) {
               uint32_t ah[4], al[4];
               split2(hA[(size_t)g * ld + k0 + t], ah[0], al[0]);
@@ -411,8 +415,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
             ++n_ready[i];
             if (pok[i]) {
               const float* psrc = px[i] + (size_t)((round[i] - 1) & 1) * a.NSL * kLstmBT * Hp;
+              // NSL independent L2 reads: issue them in batches of 8 before any add (fixed summation order)
+              const float* q = psrc + (size_t)pb * Hp + u0 + pu;
+              const size_t sstride = (size_t)kLstmBT * Hp;
               float s = 0.f;
-              for (int sl = 0; sl < a.NSL; ++sl) s += __ldcg(psrc + ((size_t)sl * kLstmBT + pb) * Hp + u0 + pu);
+              int sl = 0;
+              for (; sl + 8 <= a.NSL; sl += 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldcg(q + (size_t)(sl + j) * sstride);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += v[j];
+              }
+              for (; sl < a.NSL; ++sl) s += __ldcg(q + (size_t)sl * sstride);
               dh_reg[i] += s;
             }
           }
