@@ -114,7 +114,9 @@ int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const
  *   shift = beta - mean*scale and (optionally) save_mean / save_invstd for the backward pass.
  * vocr_bn_relu_apply_f32: a[b*sB + y*sH + x*sW + c] = relu(z[b,y,x,c]*scale[c] + shift[c])  (strides in elements,
  *   c contiguous) - the last CNN block writes the [T,B,h*C] sequence layout directly (replaces the
- *   permute+contiguous of cnnlstm.py:276).
+ *   permute+contiguous of cnnlstm.py:276).  a_hi / a_lo (both or neither; same layout as a) optionally receive the
+ *   TF32 split planes the tensor-core conv of the next block reads (saves a vocr_split_tf32_f32 pass); dz_hi / dz_lo
+ *   of vocr_bn_relu_bwd_f32 likewise.
  * vocr_bn_relu_bwd_f32: da (same strided layout) -> dz[B,H,W,C], dgamma, dbeta, dbias (= sum dz, the gradient of
  *   the conv bias in front of the BatchNorm; may be NULL).  red_ws: float64[3*C] scratch.
  */
@@ -122,12 +124,13 @@ int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamm
                          float* running_mean, float* running_var, float momentum, float eps, int training,
                          float* scale, float* shift, float* save_mean, float* save_invstd, int C,
                          vocr_stream_t stream);
-int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, int B, int H, int W,
-                           int C, long long sB, long long sH, long long sW, vocr_stream_t stream);
+int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, float* a_hi, float* a_lo,
+                           int B, int H, int W, int C, long long sB, long long sH, long long sW,
+                           vocr_stream_t stream);
 int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float* scale, const float* shift,
                          const float* save_mean, const float* save_invstd, int training, int B, int H, int W, int C,
-                         long long sB, long long sH, long long sW, float* dz, float* dgamma, float* dbeta,
-                         float* dbias, double* red_ws, vocr_stream_t stream);
+                         long long sB, long long sH, long long sW, float* dz, float* dz_hi, float* dz_lo,
+                         float* dgamma, float* dbeta, float* dbias, double* red_ws, vocr_stream_t stream);
 
 /* FractionalMaxPool2d(2, output_ratio=(0.5,0.7)) with explicit per-(sample,channel) samples[B,C,2]
  * (src/models/cnnlstm.py:127,130; ATen interval rule, random in train AND eval).  idx (int32, may be NULL) keeps the

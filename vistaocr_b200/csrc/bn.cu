@@ -8,6 +8,12 @@
 
 namespace vocr {
 
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  return __uint_as_float(t);
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, int training,
@@ -41,8 +47,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 // a[b,y,x,c] (strided) = relu(z[p,c]*scale[c] + shift[c])
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                     float* __restrict__ a, long long P, int H, int W, int C4, long long sB, long long sH,
-                     long long sW) {
+                     float* __restrict__ a, float* __restrict__ a_hi, float* __restrict__ a_lo, long long P, int H,
+                     int W, int C4, long long sB, long long sH, long long sW) {
   const long long total = P * C4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -59,7 +65,17 @@ bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scal
     r.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
     r.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
     r.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
-    *reinterpret_cast<float4*>(a + b * sB + y * sH + x * sW + (long long)c4 * 4) = r;
+    const long long o = b * sB + y * sH + x * sW + (long long)c4 * 4;
+    *reinterpret_cast<float4*>(a + o) = r;
+    if (a_hi) {  // TF32 (hi, lo) planes for the tensor-core conv that consumes this activation
+      float4 h, l;
+      h.x = tf32_rna(r.x); l.x = tf32_rna(r.x - h.x);
+      h.y = tf32_rna(r.y); l.y = tf32_rna(r.y - h.y);
+      h.z = tf32_rna(r.z); l.z = tf32_rna(r.z - h.z);
+      h.w = tf32_rna(r.w); l.w = tf32_rna(r.w - h.w);
+      *reinterpret_cast<float4*>(a_hi + o) = h;
+      *reinterpret_cast<float4*>(a_lo + o) = l;
+    }
   }
 }
 
@@ -122,7 +138,8 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const double* __restrict__ red, double inv_count,
                          int training, long long P, int H, int W, int C4, long long sB, long long sH, long long sW,
-                         long long rows_per_cta, float* __restrict__ dz, double* __restrict__ red_bias) {
+                         long long rows_per_cta, float* __restrict__ dz, float* __restrict__ dz_hi,
+                         float* __restrict__ dz_lo, double* __restrict__ red_bias) {
   extern __shared__ float s_red[];  // [256][4]
   const int rows = 256 / C4;
   const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
@@ -159,6 +176,15 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__
       o.w = sc.w * (g3 - m1[3] - (v.w - mu.w) * is.w * m2[3]);
       sb[0] += o.x; sb[1] += o.y; sb[2] += o.z; sb[3] += o.w;
       *(reinterpret_cast<float4*>(dz) + p * C4 + c4) = o;
+      if (dz_hi) {
+        float4 h, l;
+        h.x = tf32_rna(o.x); l.x = tf32_rna(o.x - h.x);
+        h.y = tf32_rna(o.y); l.y = tf32_rna(o.y - h.y);
+        h.z = tf32_rna(o.z); l.z = tf32_rna(o.z - h.z);
+        h.w = tf32_rna(o.w); l.w = tf32_rna(o.w - h.w);
+        *(reinterpret_cast<float4*>(dz_hi) + p * C4 + c4) = h;
+        *(reinterpret_cast<float4*>(dz_lo) + p * C4 + c4) = l;
+      }
     }
   }
   if (red_bias) {
@@ -199,9 +225,9 @@ extern "C" int vocr_bn_finalize_f32(const double* stats, long long count, const 
   return VOCR_OK;
 }
 
-extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, int B, int H,
-                                      int W, int C, long long sB, long long sH, long long sW,
-                                      vocr_stream_t stream_) {
+extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, float* a_hi,
+                                      float* a_lo, int B, int H, int W, int C, long long sB, long long sH,
+                                      long long sW, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long P = (long long)B * H * W;
   if (P == 0) return VOCR_OK;
@@ -210,7 +236,8 @@ extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const 
   VOCR_REQUIRE(sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
   const long long total = P * (C / 4);
   const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
-  bn_relu_apply_kernel<<<grid, 256, 0, stream>>>(z, scale, shift, a, P, H, W, C / 4, sB, sH, sW);
+  VOCR_REQUIRE((a_hi == nullptr) == (a_lo == nullptr));
+  bn_relu_apply_kernel<<<grid, 256, 0, stream>>>(z, scale, shift, a, a_hi, a_lo, P, H, W, C / 4, sB, sH, sW);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }
@@ -219,8 +246,8 @@ extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const 
 // red_ws: double[3*C] scratch.
 extern "C" int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float* scale, const float* shift,
                                     const float* save_mean, const float* save_invstd, int training, int B, int H,
-                                    int W, int C, long long sB, long long sH, long long sW, float* dz,
-                                    float* dgamma, float* dbeta, float* dbias, double* red_ws,
+                                    int W, int C, long long sB, long long sH, long long sW, float* dz, float* dz_hi,
+                                    float* dz_lo, float* dgamma, float* dbeta, float* dbias, double* red_ws,
                                     vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long P = (long long)B * H * W;
@@ -239,7 +266,7 @@ extern "C" int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float
     VOCR_CHECK_LAUNCH();
     bn_relu_bwd_apply_kernel<<<grid, 256, sizeof(float) * 256 * 4, stream>>>(
         da, z, scale, shift, save_mean, save_invstd, red_ws, 1.0 / (double)P, training, P, H, W, C4, sB, sH, sW,
-        rows_per_cta, dz, dbias ? red_ws + 2 * C : nullptr);
+        rows_per_cta, dz, dz_hi, dz_lo, dbias ? red_ws + 2 * C : nullptr);
     VOCR_CHECK_LAUNCH();
   }
   f64_to_f32_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(red_ws, dbeta, C);

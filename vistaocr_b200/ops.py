@@ -70,9 +70,9 @@ USE_TC = _os.environ.get("VOCR_TC", "1") != "0"
 class Operand:
     """A GEMM operand: the fp32 tensor plus, lazily, its (hi, lo) TF32 split (shared by every GEMM that reads it)."""
 
-    def __init__(self, t):
+    def __init__(self, t, split=None):
         self.t = _c(t)
-        self._split = None
+        self._split = split
 
     def split(self):
         if self._split is None:
@@ -193,7 +193,7 @@ def conv3x3(x, weight, bias, x_op=None):
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
     if USE_TC and Cin % 32 == 0 and Cout % 4 == 0:
-        x_op = x_op or Operand(x)
+        x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x)
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
         return _tc_conv_fwd(x_op.split(), wn.split(), bias, B, H, W, Cin, Cout), x_op
     wk, _ = _weight_layout(_c(weight.detach()), True, False)
@@ -257,9 +257,15 @@ class _ConvBNReLU(torch.autograd.Function):
         else:
             a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
             strides = (H * W * Cout, W * Cout, Cout)
-        st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), ptr(a), B, H, W, Cout, strides[0],
-                                          strides[1], strides[2], stream())
+        # the next tensor-core conv reads this activation as TF32 (hi, lo) planes: let the apply kernel write them
+        want_split = USE_TC and not seq_layout and Cout % 32 == 0
+        a_hi = torch.empty_like(a) if want_split else None
+        a_lo = torch.empty_like(a) if want_split else None
+        st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), ptr(a), ptr(a_hi), ptr(a_lo), B, H, W, Cout,
+                                          strides[0], strides[1], strides[2], stream())
         check(st, "vocr_bn_relu_apply_f32")
+        if want_split:
+            a._vocr_op = Operand(a, (a_hi, a_lo))
         ctx.save_for_backward(x, weight, z, scale, shift, mean, invstd)
         ctx.dims = (B, H, W, Cin, Cout, strides, bool(training))
         return a
@@ -275,14 +281,18 @@ class _ConvBNReLU(torch.autograd.Function):
         dbeta = torch.empty((Cout,), dtype=F32, device=dev)
         dbias = torch.empty((Cout,), dtype=F32, device=dev)
         red = torch.empty((3 * Cout,), dtype=torch.float64, device=dev)
+        want_split = USE_TC and Cout % 32 == 0 and (Cin % 32 == 0 or ctx.needs_input_grad[0])
+        dz_hi = torch.empty_like(dz) if want_split else None
+        dz_lo = torch.empty_like(dz) if want_split else None
         st = lib().vocr_bn_relu_bwd_f32(ptr(da), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
                                         int(training), B, H, W, Cout, strides[0], strides[1], strides[2], ptr(dz),
-                                        ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red), stream())
+                                        ptr(dz_hi), ptr(dz_lo), ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red),
+                                        stream())
         check(st, "vocr_bn_relu_bwd_f32")
         dx = None
-        dz_op = None
+        dz_op = Operand(dz, (dz_hi, dz_lo)) if want_split else None
         if ctx.needs_input_grad[0]:
-            dx, dz_op = conv3x3_dgrad(dz, weight)
+            dx, dz_op = conv3x3_dgrad(dz, weight, dz_op)
         dw = conv3x3_wgrad(x, dz, ctx.x_op, dz_op)
         ctx.x_op = None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
