@@ -171,11 +171,12 @@ int vocr_clamp_adam_f32(float* p, const float* g, float* m, float* v, long long 
  *   a_mn = 0: A planes [M,K] row-major (lda)      a_mn = 1: A planes stored [K,M] (lda)
  *   b_mn = 0: B planes [N,K] row-major (ldb)      b_mn = 1: B planes stored [K,N] (ldb)
  * lda, ldb multiples of 4; plane bases 16-B aligned.  C[M,N] (ldc) = op(A) op(B) (+bias[n]) (+C) (ReLU).
+ * workspace (optional): lets long reductions with few output tiles (weight gradients) run split-K over all SMs.
  * ---------------------------------------------------------------------------------------------------------- */
 int vocr_split_tf32_f32(const float* x, float* hi, float* lo, long long n, vocr_stream_t stream);
 int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_hi, const float* a_lo, int lda,
                         const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, const float* bias, int relu,
-                        int accumulate, vocr_stream_t stream);
+                        int accumulate, void* workspace, size_t workspace_bytes, vocr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3x3 convolutions on the tensor cores (4-D TMA implicit GEMM + tcgen05 3xTF32), same math as vocr_conv3x3_fwd_f32 /

@@ -51,7 +51,7 @@ PROTOTYPES = {
     "vocr_tc_conv3x3_wgrad": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_colstats_f32": (c_int, [c_p, c_ll, c_int, c_p, c_p]),
     "vocr_tc_gemm_tf32x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_int, c_p, c_int,
-                                    c_p, c_int, c_int, c_p]),
+                                    c_p, c_int, c_int, c_p, c_sz, c_p]),
 }
 
 _lib = None

@@ -7,7 +7,7 @@
 // One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
 //   warp 0   TMA producer  : 4 operand tiles (A_hi, A_lo, B_hi, B_lo; 128 x 32 fp32 = 16 KB each, SWIZZLE_128B) per
 //                            k-block into a 3-stage shared-memory ring, mbarrier expect_tx / complete_tx
-//   warp 1   MMA issuer    : allocates 128 TMEM columns, one elected lane issues 12 tcgen05.mma per k-block
+//   warp 1   MMA issuer    : allocates 512 TMEM columns, one elected lane issues 12 tcgen05.mma per k-block
 //                            (4 k-steps of 8 x 3 products), tcgen05.commit releases the stage / signals the epilogue
 //   warps 2-5 epilogue     : tcgen05.ld (32 lanes x 32 columns per warp and pass) -> bias / ReLU / accumulate -> global
 // Both operand layouts are supported without any transpose pass: K-major (the reduction dimension is contiguous in
@@ -28,13 +28,24 @@ constexpr uint32_t kTmemCols = 512;  // 3 rotating hi*hi accumulators + 1 for th
 constexpr int kTcHiAcc = 3;
 
 struct TcGemmParams {
-  float* c;
+  float* c;        // output, or the split-K partial buffer [splits][M][N] when splits > 1
   const float* bias;
   int M, N, K, ldc;
   int relu, accumulate;
   int a_mn, b_mn;  // 1 = MN-major operand
+  int kb_per_split;
 };
+constexpr int kTcChunk = 8;  // k-blocks accumulated in TMEM before the epilogue warps drain them into fp32 registers
 
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Accumulation scheme (all K): the tensor core adds into its fp32 accumulator with round-toward-zero, once per
+// instruction, by up to an ulp of the RUNNING SUM - a bias that grows linearly with the number of accumulations.
+// So (1) the two lo products go to their own accumulator (its running sum is 2^-11 smaller), and (2) hi*hi is cut
+// into chunks of kTcChunk k-blocks (32 accumulations) that rotate over 3 TMEM accumulators; the epilogue warps drain a
+// finished chunk into fp32 registers with round-to-nearest adds while the next chunk runs on another accumulator.
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -45,27 +56,31 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + kTcStages;        // [stages]
-  uint64_t* tmem_full_bar = bars + 2 * kTcStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
+  uint64_t* acc_full = bars + 2 * kTcStages;     // [3]
+  uint64_t* acc_empty = acc_full + kTcHiAcc;     // [3]
+  uint64_t* lo_full = acc_empty + kTcHiAcc;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
-  const int num_kb = (p.K + kTcBK - 1) / kTcBK;
+  const int total_kb = (p.K + kTcBK - 1) / kTcBK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int num_kb = max(0, min(total_kb, kb_begin + p.kb_per_split) - kb_begin);
+  const int num_chunks = (num_kb + kTcChunk - 1) / kTcChunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < kTcHiAcc; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
+    mbar_init(lo_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -74,13 +89,13 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kTcStages;
+        const uint32_t ph = (uint32_t)(i / kTcStages) & 1u;
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
         unsigned char* st = smem + (size_t)s * kTcStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
-        const int k0 = kb * kTcBK;
+        const int k0 = (kb_begin + i) * kTcBK;
         if (!p.a_mn) {
           tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
           tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
@@ -112,76 +127,83 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
       const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
       const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
-      // The tensor core truncates (RZ) when it adds into the fp32 accumulator, once per instruction, by up to an ulp
-      // of the RUNNING SUM - a bias that grows linearly with K.  Keep the running sums short and well scaled: the two
-      // lo products go to their own accumulator (its sum is 2^-11 smaller), hi*hi rotates over 3 accumulators by
-      // k-block; the epilogue adds the four in fp32 with round-to-nearest.
       const uint32_t tmem_lo = tmem_base + kTcHiAcc * kTcBN;
       uint32_t accum_lo = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
-        mbar_wait_or_trap(&full_bar[s], ph);
+      for (int c = 0; c < num_chunks; ++c) {
+        const int a = c % kTcHiAcc;
+        mbar_wait_or_trap(&acc_empty[a], ((uint32_t)(c / kTcHiAcc) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
+        const int i1 = min(num_kb, (c + 1) * kTcChunk);
+        for (int i = c * kTcChunk; i < i1; ++i) {
+          const int s = i % kTcStages;
+          const uint32_t ph = (uint32_t)(i / kTcStages) & 1u;
+          mbar_wait_or_trap(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
 #pragma unroll
-        for (int ks = 0; ks < kTcBK / 8; ++ks) {
-          const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, a_sbo, a_lt);
-          const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
-          const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
-          const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
-          accum_lo = 1;
-          umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_base + (uint32_t)(kb % kTcHiAcc) * kTcBN, a_hi, b_hi, idesc,
-                    (kb >= kTcHiAcc || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < kTcBK / 8; ++ks) {
+            const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
+            const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+            accum_lo = 1;
+            umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
+            umma_tf32(tmem_base + (uint32_t)a * kTcBN, a_hi, b_hi, idesc, (i > c * kTcChunk || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
+        umma_commit(&acc_full[a]);
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      umma_commit(lo_full);
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
-    mbar_wait_or_trap(tmem_full_bar, 0);
-    tc_fence_after();
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
-    const int m = m0 + lane_grp * 32 + lane;
-    float* crow = p.c + (size_t)m * p.ldc;
-    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
-#pragma unroll 1
-    const int n_hi = min(kTcHiAcc, num_kb);  // hi accumulators that were actually written
-    for (int cb = 0; cb < kTcBN; cb += 32) {
-      float r[32];
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    float sum[kTcBN];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0.f;
-      for (int acc = 0; acc <= n_hi; ++acc) {  // acc == n_hi -> the lo accumulator
-        const int which = (acc == n_hi) ? kTcHiAcc : acc;
+    for (int j = 0; j < kTcBN; ++j) sum[j] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int a = c % kTcHiAcc;
+      mbar_wait_or_trap(&acc_full[a], (uint32_t)(c / kTcHiAcc) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < kTcBN; cb += 32) {
         uint32_t t[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(which * kTcBN + cb);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
-              "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]),
-              "=r"(t[16]), "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]),
-              "=r"(t[24]), "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(lane_addr + (uint32_t)(a * kTcBN + cb), t);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(t[j]);
+        for (int j = 0; j < 32; ++j) sum[cb + j] += __uint_as_float(t[j]);
       }
-      if (m < p.M) {
+      tc_fence_before();
+      mbar_arrive_cta(&acc_empty[a]);
+    }
+    if (num_kb > 0) {
+      mbar_wait_or_trap(lo_full, 0);
+      tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + cb + j;
-          if (n >= p.N) break;
+      for (int cb = 0; cb < kTcBN; cb += 32) {
+        uint32_t t[32];
+        tmem_ld32(lane_addr + (uint32_t)(kTcHiAcc * kTcBN + cb), t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[cb + j] += __uint_as_float(t[j]);
+      }
+    }
+    const int m = m0 + lane_grp * 32 + lane;
+    if (m < p.M) {
+      const bool partial = gridDim.z > 1;  // split-K: raw partial sums, the reduce kernel applies the epilogue
+      float* crow = partial ? p.c + ((size_t)blockIdx.z * p.M + m) * p.N : p.c + (size_t)m * p.ldc;
+      const int ld_eff = partial ? p.N : p.ldc;
+      const bool vec = ((ld_eff & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+#pragma unroll
+      for (int j = 0; j < kTcBN; j += 4) {
+        const int n = n0 + j;
+        if (n < p.N) {
           float v[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float x = r[j + q];
-            if (n + q < p.N) {
+            float x = sum[j + q];
+            if (!partial && n + q < p.N) {
               if (p.bias) x += __ldg(p.bias + n + q);
               if (p.accumulate) x += crow[n + q];
               if (p.relu) x = fmaxf(x, 0.f);
@@ -203,7 +225,25 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// split-K epilogue: C = sum_z partial[z] (+bias) (+C) (relu)
+__global__ void __launch_bounds__(256)
+tc_gemm_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ c, int ldc,
+                      const float* __restrict__ bias, int relu, int accumulate) {
+  const long long total = (long long)M * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / N), n = (int)(idx - (long long)m * N);
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * total + idx];
+    if (bias) s += __ldg(bias + n);
+    float* q = c + (size_t)m * ldc + n;
+    if (accumulate) s += *q;
+    if (relu) s = fmaxf(s, 0.f);
+    *q = s;
   }
 }
 
@@ -255,10 +295,12 @@ extern "C" int vocr_split_tf32_f32(const float* x, float* hi, float* lo, long lo
 // C[M,N] = op(A) op(B) (+bias) (+C) (relu), operands pre-split into (hi, lo) planes with identical layout.
 //   a_mn = 0: A planes are [M,K] row-major (lda)      a_mn = 1: A planes are [K,M] row-major (lda)
 //   b_mn = 0: B planes are [N,K] row-major (ldb)      b_mn = 1: B planes are [K,N] row-major (ldb)
-// lda, ldb multiples of 4, plane bases 16-B aligned.
+// lda, ldb multiples of 4, plane bases 16-B aligned.  workspace (optional, 16-B aligned): enables split-K for long
+// reductions with few output tiles; any size works (the split count adapts), M*N*16 floats is ample.
 extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_hi, const float* a_lo,
                                    int lda, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc,
-                                   const float* bias, int relu, int accumulate, vocr_stream_t stream_) {
+                                   const float* bias, int relu, int accumulate, void* workspace,
+                                   size_t workspace_bytes, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VOCR_REQUIRE(M >= 0 && N >= 0 && K >= 1);
   if (M == 0 || N == 0) return VOCR_OK;
@@ -286,9 +328,27 @@ extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, cons
       return VOCR_EXECUTION_FAILED;
     attr_set = true;
   }
-  TcGemmParams p{C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0, b_mn ? 1 : 0};
-  dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM));
+  const int tiles = ceil_div(N, kTcBN) * ceil_div(M, kTcBM);
+  const int total_kb = ceil_div(K, kTcBK);
+  // split-K for long reductions that would otherwise leave most SMs idle (weight-gradient GEMMs)
+  int splits = 1;
+  if (workspace && tiles < kNumSMs && total_kb >= 32) {
+    splits = min(min(16, (2 * kNumSMs) / tiles), total_kb / 16);
+    while (splits > 1 && sizeof(float) * (size_t)M * N * splits > workspace_bytes) --splits;
+    if (splits < 1) splits = 1;
+  }
+  int kb_per_split = ceil_div(total_kb, splits);
+  splits = ceil_div(total_kb, kb_per_split);
+  TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
+                 b_mn ? 1 : 0, kb_per_split};
+  dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
   tc_gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  VOCR_CHECK_LAUNCH();
+  if (splits > 1) {
+    const long long total = (long long)M * N;
+    tc_gemm_reduce_kernel<<<(int)min((long long)4 * kNumSMs, ceil_div64(total, 256)), 256, 0, stream>>>(
+        static_cast<const float*>(workspace), splits, M, N, C, ldc, bias, relu, accumulate);
+  }
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }

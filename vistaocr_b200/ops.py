@@ -53,9 +53,13 @@ def split_tf32(t):
 def tc_gemm(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
             c_off=0):
     """Tensor-core GEMM on pre-split operands: A = (hi, lo), B = (hi, lo) (see vocr_tc_gemm_tf32x3)."""
+    ws, wsb = None, 0
+    if K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) < 148:  # long reduction, few tiles: allow split-K
+        wsb = 4 * M * N * 16
+        ws = torch.empty((wsb,), dtype=torch.uint8, device=C.device)
     st = lib().vocr_tc_gemm_tf32x3(int(a_mn), int(b_mn), M, N, K, _off(A[0], a_off), _off(A[1], a_off), lda,
                                    _off(B[0], b_off), _off(B[1], b_off), ldb, _off(C, c_off), ldc, ptr(bias),
-                                   int(relu), int(accumulate), stream())
+                                   int(relu), int(accumulate), ptr(ws), wsb, stream())
     check(st, "vocr_tc_gemm_tf32x3")
 
 
