@@ -511,7 +511,7 @@ extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, cons
   const int total_kb = ceil_div(K, kTcBK);
   // split-K for long reductions that would otherwise leave most SMs idle (weight-gradient GEMMs)
   int splits = 1;
-  if (workspace && tiles < kNumSMs && total_kb >= 32) {
+  if (workspace && tiles * 2 <= kNumSMs && total_kb >= 32) {
     splits = min(min(16, (2 * kNumSMs) / tiles), total_kb / 16);
     while (splits > 1 && sizeof(float) * (size_t)M * N * splits > workspace_bytes) --splits;
     if (splits < 1) splits = 1;
