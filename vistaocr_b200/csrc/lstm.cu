@@ -22,7 +22,6 @@
 // multiplies them by its W_hh rows (16 x 64 by 64 x H, tensor cores) into a partial dh_{t-1} for ALL units, and the
 // instance reduce-scatters the partials through L2 in a fixed order (deterministic).  dW_hh / dW_ih / db / dx are
 // tensor-core GEMMs over the saved gate gradients afterwards (host side, vistaocr_b200/ops.py).
-#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace vocr {
@@ -55,26 +54,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void red_release(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned target) {
-  if (threadIdx.x == 0) {
-    unsigned spins = 0;
-    while (ld_acquire(flag) < target) {
-      if (++spins > (1u << 26)) asm volatile("trap;");  // ~seconds: a lost peer must not hang the box
-    }
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ void signal_flag(unsigned* flag) {
-  __syncthreads();  // every thread's global writes of this step are issued
-  if (threadIdx.x == 0) {
-    __threadfence();
-    red_release(flag);
-  }
-}
-__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- tensor-core helpers: m16n8k8 TF32, operands split hi/lo in registers (3xTF32) ---------------------------------
@@ -103,11 +82,6 @@ __device__ __forceinline__ void load_w_slice(float* Ws, const float* __restrict_
     if (g < 4 && u < nu && k < H) v = __ldg(whh_dir + ((size_t)g * H + u0 + u) * H + k);
     Ws[i] = v;
   }
-}
-
-__host__ __device__ inline int lstm_hs_floats(int Hp) {
-  const int a = kLstmBT * (Hp + 4), b = 4 * kLstmBT * kLstmPartLd;
-  return a > b ? a : b;
 }
 
 // named barrier among the 256 compute threads only (the producer warps never join it)
