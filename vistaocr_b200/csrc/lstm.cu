@@ -84,6 +84,17 @@ __device__ __forceinline__ void load_w_slice(float* Ws, const float* __restrict_
   }
 }
 
+// A CTA serves the sample tiles `pair` and NBT-1-pair: batches arrive sorted by width (SortByWidthCollater), so this
+// pairs the longest tile with the shortest one and every CTA group gets about the same number of instance-steps.
+__device__ __forceinline__ int lstm_tile(int pair, int i, int NBT) { return i == 0 ? pair : NBT - 1 - pair; }
+__device__ __forceinline__ int lstm_ni(int pair, int NBT) { return (NBT - 1 - pair > pair) ? 2 : 1; }
+// steps an instance really needs: the longest sample of its tile (the rest of [0, Tmax) would be all-masked work)
+__device__ __forceinline__ int lstm_tile_tmax(const int32_t* lens, int b0, int B, int Tmax) {
+  int m = 0;
+  for (int j = b0; j < min(B, b0 + kLstmBT); ++j) m = max(m, min(lens[j], Tmax));
+  return m;
+}
+
 // named barrier among the 256 compute threads only (the producer warps never join it)
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
 
   for (int grp = blockIdx.y; grp < a.n_groups; grp += gridDim.y) {
     const int dir = grp / a.gpd, pair = grp - dir * a.gpd;
-    const int ni = min(kLstmNI, a.NBT - kLstmNI * pair);
+    const int ni = lstm_ni(pair, a.NBT);
     __syncthreads();
     load_w_slice(Ws, a.whh + (size_t)dir * 4 * H * H, H, Hp, US, u0, nu);
     for (int i = tid; i < kLstmNI * kLstmBT * ld; i += kLstmThreads) hbuf[i] = 0.f;  // padding columns stay zero
@@ -145,11 +156,13 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
       // ------------------------------ communication warp of instance i ------------------------------
       const int i = warp - 8;
       if (i < ni) {
-        const int inst = dir * a.NBT + kLstmNI * pair + i;
+        const int tile = lstm_tile(pair, i, a.NBT);
+        const int inst = dir * a.NBT + tile;
+        const int tm = lstm_tile_tmax(a.lens, tile * kLstmBT, a.B, a.Tmax);
         float* hx = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
         unsigned* flag = a.flags + inst;
         float* hs = hbuf + (size_t)i * kLstmBT * ld;
-        for (int k = 0; k < a.Tmax; ++k) {
+        for (int k = 0; k < tm; ++k) {
           if (k > 0) {
             if (k > 1) {  // hs[i] is free once the product of step k-1 has consumed it
               mbar_wait_or_trap(&empty[i], (n_empty[i] & 1u));
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
                        (uint32_t)(Hp * 4), &full[i]);
             }
           }
-          if (k + 1 < a.Tmax) {
+          if (k + 1 < tm) {
             mbar_wait_or_trap(&written[i], (n_written[i] & 1u));
             ++n_written[i];
             if (lane == 0) {
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
             }
           }
         }
-        if (a.Tmax > 1) {  // drain: the last product's release of hs[i] (keeps the phase counters in step)
+        if (tm > 1) {  // drain: the last product's release of hs[i] (keeps the phase counters in step)
           mbar_wait_or_trap(&empty[i], (n_empty[i] & 1u));
           ++n_empty[i];
         }
@@ -187,14 +200,16 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
       const int kgrp = warp >> 1, nh = warp & 1;      // K quarter, half of the 64 gate rows
       const int kq = Hp / 4;                          // K range of a quarter (Hp % 32 == 0 -> multiple of 8)
       const int pb = tid / US, pu = tid - pb * US;    // gate epilogue: one (sample, unit) pair per thread, instance
-      int b0[kLstmNI], plen[kLstmNI];
+      int b0[kLstmNI], plen[kLstmNI], tmx[kLstmNI];
       float* hx[kLstmNI];
       float c_reg[kLstmNI], h_reg[kLstmNI];
       bool pok[kLstmNI];
 #pragma unroll
       for (int i = 0; i < kLstmNI; ++i) {
-        const int inst = dir * a.NBT + kLstmNI * pair + i;
-        b0[i] = (kLstmNI * pair + i) * kLstmBT;
+        const int tile = lstm_tile(pair, i, a.NBT);
+        const int inst = dir * a.NBT + tile;
+        b0[i] = tile * kLstmBT;
+        tmx[i] = (i < ni) ? lstm_tile_tmax(a.lens, b0[i], a.B, a.Tmax) : 0;
         const int nb = min(kLstmBT, a.B - b0[i]);
         pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
         plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
@@ -205,7 +220,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
       for (int k = 0; k < a.Tmax; ++k) {
 #pragma unroll
         for (int i = 0; i < kLstmNI; ++i) {
-          if (i >= ni) continue;
+          if (i >= ni || k >= tmx[i]) continue;
           const float* hs = hbuf + (size_t)i * kLstmBT * ld;
           const bool act = pok[i] && k < plen[i];
           const int tt = act ? (dir == 0 ? k : plen[i] - 1 - k) : -1;
@@ -282,7 +297,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_fwd_kernel(LstmArgs a)
           }
           // finished samples keep publishing their last state
           if (pok[i]) hx[i][(size_t)(k & 1) * kLstmBT * Hp + (size_t)pb * Hp + u0 + pu] = h_reg[i];
-          if (k + 1 < a.Tmax) warp_arrive(&written[i]);
+          if (k + 1 < tmx[i]) warp_arrive(&written[i]);
         }
       }
     }
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
 
   for (int grp = blockIdx.y; grp < a.n_groups; grp += gridDim.y) {
     const int dir = grp / a.gpd, pair = grp - dir * a.gpd;
-    const int ni = min(kLstmNI, a.NBT - kLstmNI * pair);
+    const int ni = lstm_ni(pair, a.NBT);
     __syncthreads();
     load_w_slice(Ws, a.whh + (size_t)dir * 4 * H * H, H, Hp, US, u0, nu);
     for (int i = tid; i < kLstmNI * kLstmBT * kLstmDaLd; i += kLstmThreads) dabuf[i] = 0.f;
@@ -325,9 +340,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
       // ------------------------------ communication warp of instance i ------------------------------
       const int i = warp - 8;
       if (i < ni) {
-        unsigned* flag = a.flags + dir * a.NBT + kLstmNI * pair + i;
+        const int tile = lstm_tile(pair, i, a.NBT);
+        unsigned* flag = a.flags + dir * a.NBT + tile;
+        const int tm = lstm_tile_tmax(a.lens, tile * kLstmBT, a.B, a.Tmax);
         unsigned round = 0;
-        for (int k = a.Tmax - 1; k >= 1; --k) {
+        for (int k = tm - 1; k >= 1; --k) {
           mbar_wait_or_trap(&written[i], (n_written[i] & 1u));
           ++n_written[i];
           if (lane == 0) {
@@ -345,15 +362,17 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
       const int g = lane >> 2, t = lane & 3;
       const int pb = tid / US, pu = tid - pb * US;
       const int ntiles = Hp / 8;  // 8-column tiles of the partial product; warp w owns tiles w, w+8, ...
-      int b0[kLstmNI], plen[kLstmNI];
+      int b0[kLstmNI], plen[kLstmNI], tmx[kLstmNI];
       float* px[kLstmNI];
       float dc_reg[kLstmNI], dh_reg[kLstmNI];
       bool pok[kLstmNI];
       unsigned round[kLstmNI];
 #pragma unroll
       for (int i = 0; i < kLstmNI; ++i) {
-        const int inst = dir * a.NBT + kLstmNI * pair + i;
-        b0[i] = (kLstmNI * pair + i) * kLstmBT;
+        const int tile = lstm_tile(pair, i, a.NBT);
+        const int inst = dir * a.NBT + tile;
+        b0[i] = tile * kLstmBT;
+        tmx[i] = (i < ni) ? lstm_tile_tmax(a.lens, b0[i], a.B, a.Tmax) : 0;
         const int nb = min(kLstmBT, a.B - b0[i]);
         pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
         plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
@@ -365,7 +384,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
       for (int k = a.Tmax - 1; k >= 0; --k) {
 #pragma unroll
         for (int i = 0; i < kLstmNI; ++i) {
-          if (i >= ni) continue;
+          if (i >= ni || k >= tmx[i]) continue;
           float* das = dabuf + (size_t)i * kLstmBT * kLstmDaLd;
           // saved activations of this step: independent of the recurrence, loads issued before the wait
           const bool act = pok[i] && k < plen[i];
@@ -384,7 +403,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
             dy = dout[(tb_ * 2 + dir) * H + u0 + pu];
           }
           // 0. fold in the partial dh produced by the previous (later-in-time) step of this instance
-          if (k < a.Tmax - 1) {
+          if (k < tmx[i] - 1) {
             mbar_wait_or_trap(&ready[i], (n_ready[i] & 1u));
             ++n_ready[i];
             if (pok[i]) {
