@@ -196,6 +196,27 @@ int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const float* dz_
                           vocr_stream_t stream);
 int vocr_colstats_f32(const float* z, long long P, int C, double* stats, vocr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Device-side batch assembly.  Replaces the pixel / label copying of SortByWidthCollater
+ * (src/datautils.py:61-176): B ragged images [C,H,w_i], uploaded back to back (`packed`, element offsets
+ * `img_offsets`, tensor widths `img_widths`), land in the zero-padded batch out[B,C,H,Wout] in the order given by
+ * `order` (sorted position -> original index; the stable descending sort of the B width keys is host work); the label
+ * sequences (packed_labels, label_offsets[B+1]) are concatenated in the same order (labels_out may be NULL).  B <= 1024.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_collate_lines_f32(const float* packed, const long long* img_offsets, const int32_t* img_widths,
+                           const int32_t* order, int B, int C, int H, int Wout, float* out,
+                           const int32_t* packed_labels, const int32_t* label_offsets, int32_t* labels_out,
+                           int32_t* label_lens_out, vocr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LM-decode front end.  Replaces the host part of LmDecoder.decode (src/decoder.py:61-101):
+ * log_softmax over the alphabet, remap of model symbols to LM units (inv[u] = model index of unit u or -1, missing
+ * units get `fill` = log(1e-10)), sliced per line to its valid frames, float64.  out [sum_b lens[b], U],
+ * row_offsets[b] = first row of line b.  The WFST decoder itself (external EESEN) is out of scope.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_lm_frontend_f32(const float* logits, int T, int B, int A, const int32_t* lens, const long long* row_offsets,
+                         const int32_t* inv, int U, double fill, double* out, vocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

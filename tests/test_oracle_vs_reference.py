@@ -97,3 +97,67 @@ def test_our_model_class_mirrors_reference_state_dict_and_init(ref):
             CnnOcrModel(30)
         with pytest.raises(Exception):
             CnnOcrModel(alphabet=alpha, **dict(hp, input_line_height=45, rds_line_height=30))
+
+
+def test_collate_oracle_equals_reference_collater(ref):
+    import importlib
+    import numpy as np
+    from oracle.collate_ref import collate_ref
+    sys.path.insert(0, REF)
+    try:
+        datautils = importlib.import_module("datautils")
+    finally:
+        sys.path.remove(REF)
+    rng = np.random.default_rng(3)
+    batch = []
+    for i in range(23):
+        w = int(rng.integers(15, 200)) if i % 4 else 77  # repeated keys exercise the stable sort
+        batch.append((rng.random((1, 30, w), dtype=np.float32), rng.integers(1, 50, size=int(rng.integers(0, 9))).tolist(),
+                      {"width": w, "utt-id": "u%d" % i}))
+    want = datautils.SortByWidthCollater([(torch.from_numpy(i), t, dict(m)) for i, t, m in batch])
+    got = collate_ref(batch)
+    assert torch.equal(want[0], torch.from_numpy(got[0]))
+    assert want[1].tolist() == got[1].tolist() and want[2].tolist() == got[2].tolist()
+    assert want[3].tolist() == got[3].tolist()
+    assert want[4]["utt-ids"] == [batch[i][2]["utt-id"] for i in got[4]]
+    sys.modules.pop("datautils", None)
+
+
+def test_lm_frontend_oracle_equals_reference_lmdecoder(ref):
+    """LmDecoder.__init__ needs the external eesen binding; build the object without it, fill in the attributes its
+    decode() reads (decoder.py:36-59) and capture what it submits to the executor."""
+    import importlib
+    import numpy as np
+    from oracle.lm_frontend_ref import lm_remap_ref
+    sys.path.insert(0, REF)
+    try:
+        decoder = importlib.import_module("decoder")
+    finally:
+        sys.path.remove(REF)
+    A = 17
+    chars = ["<ctc-blank>"] + ["u%04x" % (0x61 + i) for i in range(A - 1)]
+    alpha = ref.Alphabet(chars)
+    lm_units = [chars[3], chars[9], "u4e00", chars[1], "u4e01", chars[16]]
+    units = ["<ctc-blank>"] + lm_units
+    d = decoder.LmDecoder.__new__(decoder.LmDecoder)
+    d.alphabet = alpha
+    d.lmidx_to_char = units
+    d.lmchar_to_idx = dict(zip(units, range(len(units))))
+    d.lm_swap_idxs_modelidx = [m for m in range(A) if chars[m] in d.lmchar_to_idx]
+    d.lm_swap_idxs_lmidx = [d.lmchar_to_idx[chars[m]] for m in d.lm_swap_idxs_modelidx]
+
+    class Capture:
+        def __init__(self):
+            self.got = []
+
+        def submit(self, fn, probs, uttid, uxxxx):
+            self.got.append(probs)
+
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.normal(size=(11, 3, A)).astype(np.float32))
+    lens = [11, 7, 0]
+    cap = Capture()
+    d.decode(cap, x, lens, ["a", "b", "c"])
+    want = lm_remap_ref(x, lens, alpha.idx_to_char, lm_units)
+    for g, w in zip(cap.got, want):
+        assert g.dtype == np.float64 and np.array_equal(g, w)
