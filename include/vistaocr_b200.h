@@ -217,6 +217,14 @@ int vocr_collate_lines_f32(const float* packed, const long long* img_offsets, co
 int vocr_lm_frontend_f32(const float* logits, int T, int B, int A, const int32_t* lens, const long long* row_offsets,
                          const int32_t* inv, int U, double fill, double* out, vocr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Batched edit distance.  Replaces the NumPy double loop of edit_distance
+ * (src/textutils.py:264-287) behind compute_cer_wer (:326-351): P pairs of int32 sequences, unit costs, exact.
+ *   a_flat/a_off[P+1], b_flat/b_off[P+1]: concatenated sequences + offsets;  max_n/max_m: length bounds;  dist [P].
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_edit_distance_i32(const int32_t* a_flat, const int32_t* a_off, const int32_t* b_flat, const int32_t* b_off,
+                           int P, int max_n, int max_m, int32_t* dist, vocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

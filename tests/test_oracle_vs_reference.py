@@ -161,3 +161,30 @@ def test_lm_frontend_oracle_equals_reference_lmdecoder(ref):
     want = lm_remap_ref(x, lens, alpha.idx_to_char, lm_units)
     for g, w in zip(cap.got, want):
         assert g.dtype == np.float64 and np.array_equal(g, w)
+
+
+def test_scoring_oracle_equals_reference_textutils():
+    """textutils.py cannot be imported (ICU, absolute paths): lift the three pure functions out of its source."""
+    import ast
+    import numpy as np
+    from oracle.scoring_ref import compute_cer_wer_ref, edit_distance_ref
+    from vistaocr_b200.scoring import form_tokenized_words as ours_ftw
+    src = open(os.path.join(REF, "textutils.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("edit_distance", "form_tokenized_words", "compute_cer_wer"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "textutils.py", "exec"), ns)
+    rng = np.random.default_rng(5)
+    alphabet = ["u0020", "u002e", "u0031", "u002c", "u0661"] + ["u%04x" % (0x61 + i) for i in range(12)]
+    for _ in range(30):
+        ref = " ".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), size=int(rng.integers(3, 40))))
+        hyp = " ".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), size=int(rng.integers(0, 40))))
+        assert ns["edit_distance"](hyp.split(" "), ref.split(" ")) == edit_distance_ref(hyp.split(" "), ref.split(" "))
+        assert ns["form_tokenized_words"](ref.split(" ")) == ours_ftw(ref.split(" "))
+        assert ns["form_tokenized_words"](ref.split(" "), with_spaces=True) == ours_ftw(ref.split(" "), with_spaces=True)
+        try:
+            want = ns["compute_cer_wer"](hyp, ref)
+        except ZeroDivisionError:
+            continue
+        assert want == compute_cer_wer_ref(hyp, ref, ours_ftw)
