@@ -176,3 +176,55 @@ def test_train_step_with_fused_optimizer(cuda):
         # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the gradient is not ~0
         mask = g.abs() > 1e-6
         assert (p.detach().double().cpu() - p1)[mask].abs().max().item() <= 5e-5
+
+
+def test_full_size_cfg2_against_oracle_on_gpu(cuda):
+    """BASELINE cfg2 at FULL size (line height 60 -> rds 30, batch 64, widths up to 1200, D128 / 3x512 BiLSTM,
+    alphabet 96): the oracle restatement (plain torch ops, fp32 with TF32 disabled) is run on the GPU so that it
+    finishes in seconds, and the whole path - logits, lengths, CTC loss, transcripts, parameter gradients - is
+    compared at the size the benchmark runs.  Size-independent properties ride along: padded frames equal the
+    prob-layer bias exactly, outputs beyond a line's length carry no gradient."""
+    from vistaocr_b200 import CTCLoss
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    hp = dict(input_line_height=60, rds_line_height=30, lstm_input_dim=128, num_lstm_layers=3,
+              num_lstm_hidden_units=512, p_lstm_dropout=0.0)
+    A, B = 96, 64
+    sd = M.make_state_dict(hp, A, seed=77)
+    model = _model(hp, A, sd, cuda)
+    rng = np.random.default_rng(77)
+    x, widths, labels, label_lens = M.synth_batch(rng, B, 60, 300, 1200, A, 20, 60, n_rds=1)
+    u1 = torch.from_numpy(rng.random((B, 64, 2)).astype(np.float32))
+    u2 = torch.from_numpy(rng.random((B, 128, 2)).astype(np.float32))
+    model.cnn[6]._random_samples, model.cnn[13]._random_samples = u1, u2
+    model.train()
+    xg = torch.from_numpy(x).to(cuda)
+    logits, lens = model(xg, torch.from_numpy(widths))
+    loss = CTCLoss(host_cost=False)(logits, torch.from_numpy(labels), lens, torch.from_numpy(label_lens))
+    loss.backward()
+    # oracle on the GPU
+    sdg = {k: v.to(cuda) for k, v in sd.items()}
+    for k, v in sdg.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    want, wlens = M.forward_ref(sdg, xg, widths, hp, (u1.to(cuda), u2.to(cuda)), training=True, bn_updates={})
+    assert lens.tolist() == wlens.tolist() and logits.shape == want.shape
+    _close(logits, want, "cfg2 logits", rtol=5e-5)
+    wloss = M.ctc_sum_ref(want.cpu(), labels, wlens, label_lens)
+    assert abs(loss.item() - wloss.item()) <= 5e-5 * abs(wloss.item())
+    wloss_g = torch.nn.functional.ctc_loss(want.log_softmax(2), torch.from_numpy(labels).long().to(cuda),
+                                           wlens.long().to(cuda), torch.from_numpy(label_lens).long().to(cuda),
+                                           blank=0, reduction="sum", zero_infinity=True)
+    wloss_g.backward()
+    hyp = model.decode_without_lm(logits, lens, uxxxx=True)
+    assert hyp == decode_loop(logits.detach().cpu().numpy(), lens.numpy(), model.alphabet.idx_to_char, uxxxx=True)
+    bias = model.prob_layer[0].bias
+    for b in (B - 1, B // 2):
+        if lens[b] < logits.shape[0]:
+            assert torch.equal(logits[lens[b]:, b], bias.expand(logits.shape[0] - int(lens[b]), -1))
+    for k, p in model.named_parameters():
+        if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
+            continue
+        w = sdg[k].grad
+        # full-size tensors: routing flips (ReLU / max-pool ties) touch a few elements among ~10^6 contributions
+        _close(p.grad, w, "cfg2 grad " + k, rtol=2e-3 if _grad_rtol(k) > 1e-3 else 1e-3, atol=1e-5)
