@@ -202,29 +202,41 @@ def test_full_size_cfg2_against_oracle_on_gpu(cuda):
     logits, lens = model(xg, torch.from_numpy(widths))
     loss = CTCLoss(host_cost=False)(logits, torch.from_numpy(labels), lens, torch.from_numpy(label_lens))
     loss.backward()
-    # oracle on the GPU
-    sdg = {k: v.to(cuda) for k, v in sd.items()}
-    for k, v in sdg.items():
-        if v.is_floating_point() and "running" not in k:
-            v.requires_grad_(True)
-    want, wlens = M.forward_ref(sdg, xg, widths, hp, (u1.to(cuda), u2.to(cuda)), training=True, bn_updates={})
+    # oracle on the GPU, twice: float32 (the reference's arithmetic) and float64 (the exact answer)
+    def oracle(dtype):
+        sdg = {k: (v.to(cuda, dtype) if v.is_floating_point() else v.to(cuda)) for k, v in sd.items()}
+        for k, v in sdg.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+        out, olens = M.forward_ref(sdg, xg.to(dtype), widths, hp, (u1.to(cuda), u2.to(cuda)), training=True,
+                                   bn_updates={})
+        ol = torch.nn.functional.ctc_loss(out.log_softmax(2), torch.from_numpy(labels).long().to(cuda),
+                                          olens.long().to(cuda), torch.from_numpy(label_lens).long().to(cuda),
+                                          blank=0, reduction="sum", zero_infinity=True)
+        ol.backward()
+        return out.detach(), olens, ol.item(), {k: v.grad for k, v in sdg.items() if v.is_floating_point() and v.grad is not None}
+
+    want, wlens, wloss, wgrad = oracle(torch.float32)
+    w64, _, wloss64, wgrad64 = oracle(torch.float64)
     assert lens.tolist() == wlens.tolist() and logits.shape == want.shape
-    _close(logits, want, "cfg2 logits", rtol=5e-5)
-    wloss = M.ctc_sum_ref(want.cpu(), labels, wlens, label_lens)
-    assert abs(loss.item() - wloss.item()) <= 5e-5 * abs(wloss.item())
-    wloss_g = torch.nn.functional.ctc_loss(want.log_softmax(2), torch.from_numpy(labels).long().to(cuda),
-                                           wlens.long().to(cuda), torch.from_numpy(label_lens).long().to(cuda),
-                                           blank=0, reduction="sum", zero_infinity=True)
-    wloss_g.backward()
+    _close(logits, w64, "cfg2 logits vs float64", rtol=5e-5)
+    assert abs(loss.item() - wloss64) <= 5e-5 * abs(wloss64)
     hyp = model.decode_without_lm(logits, lens, uxxxx=True)
     assert hyp == decode_loop(logits.detach().cpu().numpy(), lens.numpy(), model.alphabet.idx_to_char, uxxxx=True)
     bias = model.prob_layer[0].bias
     for b in (B - 1, B // 2):
         if lens[b] < logits.shape[0]:
             assert torch.equal(logits[lens[b]:, b], bias.expand(logits.shape[0] - int(lens[b]), -1))
+    # gradients: no further from float64 than twice the reference arithmetic's own distance (max-pool / ReLU routing
+    # flips dominate the upstream tensors at this size), and within 1e-3 of the tensor scale otherwise
+    worst = 0.0
     for k, p in model.named_parameters():
         if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
             continue
-        w = sdg[k].grad
-        # full-size tensors: routing flips (ReLU / max-pool ties) touch a few elements among ~10^6 contributions
-        _close(p.grad, w, "cfg2 grad " + k, rtol=2e-3 if _grad_rtol(k) > 1e-3 else 1e-3, atol=1e-5)
+        g64 = wgrad64[k]
+        scale = g64.abs().max().item()
+        ours = (p.grad.double() - g64).abs().max().item()
+        ref32 = (wgrad[k].double() - g64).abs().max().item()
+        worst = max(worst, ours / scale)
+        assert ours <= max(1e-3 * scale, 2.0 * ref32) + 1e-6, (k, ours / scale, ref32 / scale)
+    assert worst <= 2e-2
