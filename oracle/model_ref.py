@@ -48,22 +48,23 @@ def fmp_starts(u, in_size, out_size, dtype=np.float32):
     return seq
 
 
-def fmp_ref(x, samples):
+def fmp_ref(x, samples, interval_dtype=np.float32):
     """FractionalMaxPool2d(2, output_ratio=(0.5,0.7)) with explicit per-(n,c) samples [N,C,2]
-    (samples[...,0] drives W, [...,1] drives H), via the formula above.  x: [N,C,H,W]."""
+    (samples[...,0] drives W, [...,1] drives H), via the formula above.  x: [N,C,H,W].  The window positions are
+    computed in `interval_dtype` - float32 is what the (fp32) reference model does; keeping it for a float64 `x` gives
+    the float64 evaluation of the SAME function (F.fractional_max_pool2d on float64 input would move some windows)."""
     N, C, H, W = x.shape
     Ho, Wo = int(H * 0.5), int(W * 0.7)
-    np_dt = np.float32 if x.dtype == torch.float32 else np.float64
-    out = torch.empty((N, C, Ho, Wo), dtype=x.dtype)
-    s = samples.detach().cpu().numpy()
+    s = samples.detach().cpu().numpy().astype(np.float32)
+    planes = []
     for n in range(N):
         for c in range(C):
-            ws = torch.from_numpy(fmp_starts(s[n, c, 0], W, Wo, np_dt))
-            hs = torch.from_numpy(fmp_starts(s[n, c, 1], H, Ho, np_dt))
+            ws = torch.from_numpy(fmp_starts(s[n, c, 0], W, Wo, interval_dtype)).to(x.device)
+            hs = torch.from_numpy(fmp_starts(s[n, c, 1], H, Ho, interval_dtype)).to(x.device)
             p = x[n, c]
             rows = torch.maximum(p[hs], p[hs + 1])
-            out[n, c] = torch.maximum(rows[:, ws], rows[:, ws + 1])
-    return out
+            planes.append(torch.maximum(rows[:, ws], rows[:, ws + 1]))
+    return torch.stack(planes).view(N, C, Ho, Wo)
 
 
 def cnn_ref(sd, x, n_rds, pool_samples, training, bn_updates=None, prefix="cnn."):
@@ -86,7 +87,10 @@ def cnn_ref(sd, x, n_rds, pool_samples, training, bn_updates=None, prefix="cnn."
         x = F.relu(x)
         if k in POOL_AFTER:
             u = pool_samples[POOL_AFTER.index(k)]
-            x = F.fractional_max_pool2d(x, 2, output_ratio=(0.5, 0.7), _random_samples=u.to(x.dtype))
+            if x.dtype == torch.float32:
+                x = F.fractional_max_pool2d(x, 2, output_ratio=(0.5, 0.7), _random_samples=u.to(x.dtype))
+            else:  # float64 twin of the fp32 model: same (float32-computed) windows
+                x = fmp_ref(x, u)
     return x
 
 
