@@ -317,26 +317,16 @@ __global__ void __launch_bounds__(256 + 32 * NI, 1) bilstm_fwd_kernel(LstmArgs a
             PF_ADD(pf_epi, c3, c3b);
           }
           PF_T(c4);
+          float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f;
           if (act) {
-            const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_(pre[3]);
-            const float c = fmaf(fg, c_reg[i], ig * gg);
-            const float h = og * tanhf(c);
-            c_reg[i] = c;
-            h_reg[i] = h;
-            const size_t tb_ = (size_t)tt * a.B + b0[i] + pb;
-            a.out[(tb_ * 2 + dir) * H + u0 + pu] = h;
-            if (a.gates) {
-              float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
-              gp[0] = ig;
-              gp[(size_t)H] = fg;
-              gp[(size_t)2 * H] = gg;
-              gp[(size_t)3 * H] = og;
-            }
-            if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + pu] = c;
+            ig = sigmoidf_(pre[0]); fg = sigmoidf_(pre[1]); gg = tanhf(pre[2]); og = sigmoidf_(pre[3]);
+            c_reg[i] = fmaf(fg, c_reg[i], ig * gg);
+            h_reg[i] = og * tanhf(c_reg[i]);
           }
           PF_T(c5);
           PF_ADD(pf_epi, c4, c5);
-          // finished samples keep publishing their last state
+          // publish first (finished samples keep publishing their last state): the release that follows `written`
+          // then does not have to wait for the bulkier stores of this step's outputs below
           if (pok[i]) {
             __half* row = reinterpret_cast<__half*>(hx[i] + (size_t)(k & 1) * kLstmBT * Hp + (size_t)pb * Hp);
             __half hi, lo;
@@ -345,6 +335,18 @@ __global__ void __launch_bounds__(256 + 32 * NI, 1) bilstm_fwd_kernel(LstmArgs a
             row[Hp + u0 + pu] = lo;
           }
           if (k + 1 < tmx[i]) warp_arrive(&written[i]);
+          if (act) {
+            const size_t tb_ = (size_t)tt * a.B + b0[i] + pb;
+            a.out[(tb_ * 2 + dir) * H + u0 + pu] = h_reg[i];
+            if (a.gates) {
+              float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + pu;
+              gp[0] = ig;
+              gp[(size_t)H] = fg;
+              gp[(size_t)2 * H] = gg;
+              gp[(size_t)3 * H] = og;
+            }
+            if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + pu] = c_reg[i];
+          }
           PF_T(c6);
           PF_ADD(pf_pub, c5, c6);
         }
@@ -471,6 +473,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
         dh_reg[i] = 0.f;
         round[i] = 0;
       }
+#ifdef VOCR_LSTM_PROF
+      long long pf_wait = 0, pf_red = 0, pf_grad = 0, pf_frag = 0, pf_prod = 0, pf_store = 0, pf_t0 = clock64();
+#endif
       for (int k = a.Tmax - 1; k >= 0; --k) {
 #pragma unroll
         for (int i = 0; i < kLstmNI; ++i) {
@@ -493,17 +498,31 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
             dy = dout[(tb_ * 2 + dir) * H + u0 + pu];
           }
           // 0. fold in the partial dh produced by the previous (later-in-time) step of this instance
+          PF_T(c0);
           if (k < tmx[i] - 1) {
             mbar_wait_or_trap(&ready[i], (n_ready[i] & 1u));
             ++n_ready[i];
+            PF_T(c1);
+            PF_ADD(pf_wait, c0, c1);
             if (pok[i]) {
               const float* q = pbuf + (size_t)i * blk + (size_t)pb * US + pu;
               const int sstride = kLstmBT * US;
-              float s = 0.f;
-              for (int sl = 0; sl < a.NSL; ++sl) s += q[(size_t)sl * sstride];  // fixed summation order
+              float s = 0.f;  // fixed summation order; loads batched by 8 ahead of the dependent adds
+              int sl = 0;
+              for (; sl + 8 <= a.NSL; sl += 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = q[(size_t)(sl + j) * sstride];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += v[j];
+              }
+              for (; sl < a.NSL; ++sl) s += q[(size_t)sl * sstride];
               dh_reg[i] += s;
             }
+            PF_T(c2);
+            PF_ADD(pf_red, c1, c2);
           }
+          PF_T(c3);
           // 1. gate gradients of this slice's units at step k
           float da[4] = {0.f, 0.f, 0.f, 0.f};
           if (act) {
@@ -527,6 +546,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
 #pragma unroll
             for (int q = 0; q < 4; ++q) das[(size_t)pb * kLstmDaLd + q * US + pu] = da[q];
           }
+          PF_T(c4);
+          PF_ADD(pf_grad, c3, c4);
           compute_sync();
           // 2. partial dh_{k-1}[16, :] = das[16, 0:64] . Ws[0:64, :]  (tensor cores) -> px[round&1][consumer][slice]
           //    A fragments: rows g and g+8, lane t owns k = 16*ks + 4t .. +3 of every k16 step (B uses the same map)
@@ -536,7 +557,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
             x0[ks] = *reinterpret_cast<const float4*>(das + (size_t)g * kLstmDaLd + ks * 16 + 4 * t);
             x1[ks] = *reinterpret_cast<const float4*>(das + (size_t)(g + 8) * kLstmDaLd + ks * 16 + 4 * t);
           }
-          compute_sync();  // das[i] may be rewritten by the next step of this instance
+          // (das[i] is rewritten only after ready[i] of the next step, i.e. after every warp's `written` arrival below)
           float m0 = 0.f, m1 = 0.f;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -568,47 +589,84 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
             pack(x0[ks].z, x0[ks].w, s0, ah[ks][2], al[ks][2]);
             pack(x1[ks].z, x1[ks].w, s1, ah[ks][3], al[ks][3]);
           }
+          PF_T(c5);
+          PF_ADD(pf_frag, c4, c5);
           float* pdst = px[i] + (size_t)(round[i] & 1) * a.NSL * blk + (size_t)slice * kLstmBT * US;
-          for (int nt = warp; nt < ntiles; nt += 8) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acl[4] = {0.f, 0.f, 0.f, 0.f};
-            const uint32_t* wB = Wt + (size_t)(nt * 8 + g) * kBwdWtLd + 2 * t;
+          // four column tiles at a time: 12 independent accumulator chains keep the tensor pipe busy.
+          // (A "fragment order" block layout with one 16-byte store per lane measured SLOWER than these 8-byte
+          // stores: 7.25 vs 6.09 us/step at H=512, B=64.)
+          for (int base = 0; base < ntiles; base += 32) {
+            int ntj[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ntj[j] = base + warp + 8 * j;
+            // branch-free: a tile index past the end (small H) is redirected to tile 0 and its result dropped below
+            const uint32_t* wB[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              wB[j] = Wt + (size_t)((ntj[j] < ntiles ? ntj[j] : 0) * 8 + g) * kBwdWtLd + 2 * t;
+            float acc[4][4], acl[4][4], acm[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[j][q] = acl[j][q] = acm[j][q] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint2 wh = *reinterpret_cast<const uint2*>(wB + ks * 8);
-              const uint2 wl = *reinterpret_cast<const uint2*>(wB + kLstmRows / 2 + ks * 8);
-              const uint32_t bh[2] = {wh.x, wh.y}, bl[2] = {wl.x, wl.y};
-              mma_f16(acl, al[ks], bh);
-              mma_f16(acl, ah[ks], bl);
-              mma_f16(acc, ah[ks], bh);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint2 wh = *reinterpret_cast<const uint2*>(wB[j] + ks * 8);
+                const uint2 wl = *reinterpret_cast<const uint2*>(wB[j] + kLstmRows / 2 + ks * 8);
+                const uint32_t bh[2] = {wh.x, wh.y}, bl[2] = {wl.x, wl.y};
+                mma_f16(acl[j], al[ks], bh);
+                mma_f16(acm[j], ah[ks], bl);
+                mma_f16(acc[j], ah[ks], bh);
+              }
             }
-            const float v00 = fmaf(acl[0], 1.f / kLoScale, acc[0]) * r0, v01 = fmaf(acl[1], 1.f / kLoScale, acc[1]) * r0;
-            const float v10 = fmaf(acl[2], 1.f / kLoScale, acc[2]) * r1, v11 = fmaf(acl[3], 1.f / kLoScale, acc[3]) * r1;
-            // columns col, col+1 (units of the layer) -> consumer slice cs, unit offset cu inside it
-            const int col = nt * 8 + 2 * t;
-            const int cs = (int)(((float)col + 0.5f) * inv_us), cu = col - cs * US;
-            if (cs < a.NSL) {
-              float* d0 = pdst + (size_t)cs * blk + (size_t)g * US + cu;
-              float* d1 = d0 + (size_t)8 * US;
-              if ((US & 1) == 0) {
-                *reinterpret_cast<float2*>(d0) = make_float2(v00, v01);
-                *reinterpret_cast<float2*>(d1) = make_float2(v10, v11);
-              } else {
-                d0[0] = v00;
-                d1[0] = v10;
-                // the odd column may belong to the next consumer slice
-                const int cs1 = (cu + 1 == US) ? cs + 1 : cs, cu1 = (cu + 1 == US) ? 0 : cu + 1;
-                if (cs1 < a.NSL) {
-                  pdst[(size_t)cs1 * blk + (size_t)g * US + cu1] = v01;
-                  pdst[(size_t)cs1 * blk + (size_t)(g + 8) * US + cu1] = v11;
+            PF_T(c5b);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int nt = ntj[j];
+              if (nt >= ntiles) continue;
+              const float v00 = fmaf(acl[j][0] + acm[j][0], 1.f / kLoScale, acc[j][0]) * r0;
+              const float v01 = fmaf(acl[j][1] + acm[j][1], 1.f / kLoScale, acc[j][1]) * r0;
+              const float v10 = fmaf(acl[j][2] + acm[j][2], 1.f / kLoScale, acc[j][2]) * r1;
+              const float v11 = fmaf(acl[j][3] + acm[j][3], 1.f / kLoScale, acc[j][3]) * r1;
+              // columns col, col+1 (units of the layer) -> consumer slice cs, unit offset cu inside it
+              const int col = nt * 8 + 2 * t;
+              const int cs = (int)(((float)col + 0.5f) * inv_us), cu = col - cs * US;
+              if (cs < a.NSL) {
+                float* d0 = pdst + (size_t)cs * blk + (size_t)g * US + cu;
+                float* d1 = d0 + (size_t)8 * US;
+                if ((US & 1) == 0) {
+                  *reinterpret_cast<float2*>(d0) = make_float2(v00, v01);
+                  *reinterpret_cast<float2*>(d1) = make_float2(v10, v11);
+                } else {
+                  d0[0] = v00;
+                  d1[0] = v10;
+                  // the odd column may belong to the next consumer slice
+                  const int cs1 = (cu + 1 == US) ? cs + 1 : cs, cu1 = (cu + 1 == US) ? 0 : cu + 1;
+                  if (cs1 < a.NSL) {
+                    pdst[(size_t)cs1 * blk + (size_t)g * US + cu1] = v01;
+                    pdst[(size_t)cs1 * blk + (size_t)(g + 8) * US + cu1] = v11;
+                  }
                 }
               }
             }
+            PF_T(c5c);
+            PF_ADD(pf_store, c5b, c5c);
           }
           // 3. publish through the communication warp; the reduce-scatter happens at the top of the next step
           warp_arrive(&written[i]);
           ++round[i];
+          PF_T(c6);
+          PF_ADD(pf_prod, c5, c6);
         }
       }
+#ifdef VOCR_LSTM_PROF
+      if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 255))
+        printf("lstm bwd prof tid %d: total %lld  wait %lld  reduce %lld  grad %lld  sync+frag %lld  prod+store %lld (store %lld) (cycles), Tmax %d\n",
+               tid, clock64() - pf_t0, pf_wait, pf_red, pf_grad, pf_frag, pf_prod, pf_store, a.Tmax);
+#endif
     }
   }
 }
@@ -622,7 +680,7 @@ using namespace vocr;
 static int lstm_geometry(int B, int H, LstmArgs* a, size_t* smem, int* grid_y, bool bwd, int* variant) {
   if (H < 1 || H > 32 * kLstmMaxUS) return VOCR_INVALID_VALUE;
   a->NBT = ceil_div(B, kLstmBT);
-  *variant = (!bwd && a->NBT >= 3) ? 1 : 0;
+  *variant = 0;
   if (const char* e = getenv("VOCR_LSTM_VARIANT")) *variant = (!bwd && atoi(e) == 1) ? 1 : 0;
   const int slices = *variant ? 64 : 32, ni = *variant ? 4 : kLstmNI, rows = *variant ? 32 : kLstmRows;
   a->US = ceil_div(H, slices);
