@@ -75,7 +75,7 @@ class Operand:
     """A GEMM operand: the fp32 tensor plus, lazily, its (hi, lo) TF32 split (shared by every GEMM that reads it)."""
 
     def __init__(self, t, split=None):
-        self.t = _c(t)
+        self.t = _c(t) if t is not None else None  # None: split-only operand (see _ConvBNReLU.forward)
         self._split = split
 
     def split(self):
@@ -269,7 +269,9 @@ class _ConvBNReLU(torch.autograd.Function):
                                           strides[0], strides[1], strides[2], stream())
         check(st, "vocr_bn_relu_apply_f32")
         if want_split:
-            a._vocr_op = Operand(a, (a_hi, a_lo))
+            # split-only: an Operand that held `a` would form a reference cycle (a -> attribute -> a) and keep the
+            # activation and both planes alive until Python's cyclic GC runs - several GB per step
+            a._vocr_op = Operand(None, (a_hi, a_lo))
         ctx.save_for_backward(x, weight, z, scale, shift, mean, invstd)
         ctx.dims = (B, H, W, Cin, Cout, strides, bool(training))
         return a
