@@ -179,6 +179,28 @@ int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_
                         int accumulate, void* workspace, size_t workspace_bytes, vocr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * FP16 pair operands: the same error-compensated three-product scheme on tcgen05.mma kind::f16 - twice the K per
+ * instruction and half the operand bytes of the TF32 planes, same fp32-level accuracy (22 significant bits).
+ * vocr_split_f16_f32: x[n] -> hi = fp16(x 2^e), lo = fp16((x 2^e - hi) 2^11), e chosen so that bound 2^e lies in
+ *   [2^14, 2^15).  state: device int32[2], [0] receives e, [1] is scratch.  bound: optional device float >= max|x|
+ *   (when NULL an absmax pass computes it).  Everything stays on the stream - no host synchronisation.
+ * vocr_tc_gemm_f16x3 / vocr_tc_conv3x3_fwd_f16 / vocr_tc_conv3x3_wgrad_f16: as their TF32 namesakes, taking the planes
+ *   and the device exponent of each operand; lda / ldb multiples of 8, Cin % 64 == 0 (and Cout % 64 == 0 for wgrad).
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_split_f16_f32(const float* x, long long n, const float* bound, int32_t* state, uint16_t* hi, uint16_t* lo,
+                       vocr_stream_t stream);
+int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const uint16_t* a_hi, const uint16_t* a_lo, int lda,
+                       const int32_t* exp_a, const uint16_t* b_hi, const uint16_t* b_lo, int ldb, const int32_t* exp_b,
+                       float* C, int ldc, const float* bias, int relu, int accumulate, void* workspace,
+                       size_t workspace_bytes, vocr_stream_t stream);
+int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* w_hi,
+                            const uint16_t* w_lo, const int32_t* exp_w, const float* bias, float* z, int B, int H, int W,
+                            int Cin, int Cout, vocr_stream_t stream);
+int vocr_tc_conv3x3_wgrad_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* dz_hi,
+                              const uint16_t* dz_lo, const int32_t* exp_dz, float* dw, int B, int H, int W, int Cin,
+                              int Cout, void* workspace, size_t workspace_bytes, vocr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * 3x3 convolutions on the tensor cores (4-D TMA implicit GEMM + tcgen05 3xTF32), same math as vocr_conv3x3_fwd_f32 /
  * vocr_conv3x3_wgrad_f32 (src/models/cnnlstm.py:124-134 -> cuDNN).  Activations arrive as (hi, lo) TF32 planes
  * (vocr_split_tf32_f32), NHWC.

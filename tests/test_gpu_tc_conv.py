@@ -44,6 +44,27 @@ def test_tc_conv_fwd_dgrad_wgrad(cuda, B, H, W, Cin, Cout):
     close(dw, wr.grad, "wgrad")
 
 
+@pytest.mark.parametrize("xs,ds", [(1e-4, 1e-7), (300.0, 1e3)])
+def test_tc_conv_f16_pairs_scaled_operands(cuda, xs, ds):
+    """FP16 pair path (Cin, Cout % 64 == 0) with operand magnitudes outside FP16's range."""
+    from vistaocr_b200 import ops
+    assert ops.USE_F16
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cin, Cout = 2, 9, 75, 64, 128
+    x = torch.randn(B, Cin, H, W, generator=g) * xs
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3.0 * Cin ** 0.5)
+    dz = torch.randn(B, Cout, H, W, generator=g) * ds
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    zr = F.conv2d(xr, wr, None, padding=1)
+    zr.backward(dz.double())
+    xo, wo, dzo = nhwc(x).to(cuda), w.to(cuda), nhwc(dz).to(cuda)
+    z, x_op = ops.conv3x3(xo, wo, None)
+    close(nchw(z), zr, "fwd")
+    dx, dz_op = ops.conv3x3_dgrad(dzo, wo)
+    close(nchw(dx), xr.grad, "dgrad")
+    close(ops.conv3x3_wgrad(xo, dzo, x_op, dz_op), wr.grad, "wgrad")
+
+
 def test_wgrad_long_reduction_keeps_fp32_accuracy(cuda):
     """~1.2e5 pixels with a non-zero mean (the worst case for round-toward-zero accumulation)."""
     from vistaocr_b200 import ops

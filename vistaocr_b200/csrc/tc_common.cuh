@@ -25,6 +25,42 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Operand element type of a kernel instantiation.  F16 = false: TF32 planes (hi, lo), K = 8 per instruction.
+// F16 = true: FP16 pair planes (hi, lo * 2^11) of x * 2^e, K = 16 per instruction - the same 32 bytes of K per
+// instruction and per swizzle row, so every tile keeps its byte geometry and the k loop covers twice the elements.
+template <bool F16>
+struct TcElem {
+  static constexpr int kBK = F16 ? 64 : 32;                       // K elements per 128-byte swizzle row (one k-block)
+  static constexpr uint32_t kFmt = F16 ? 0u : 2u;                 // instruction-descriptor operand format
+  // MN-major operand tiles (the reduction index is the row): TMA box / UMMA descriptor constants
+  static constexpr int kMnBox = F16 ? 64 : 32;                    // M/N elements per box (128 bytes)
+  static constexpr uint32_t kMnBoxBytes = F16 ? 8192u : 4096u;    // box = kMnBox x kBK k rows
+  static constexpr uint32_t kMnSbo = F16 ? 1024u : 512u;          // stride between k groups (8 / 4 rows of 128 B)
+  static constexpr uint32_t kMnStep = F16 ? 2048u : 1024u;        // one instruction's k rows (16 / 8) x 128 B
+  static constexpr uint32_t kMnLayout = F16 ? 2u : 1u;            // SWIZZLE_128B / SWIZZLE_128B_BASE32B
+  static __device__ __forceinline__ void mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if constexpr (F16) umma_f16(tmem_c, da, db, idesc, acc);
+    else umma_tf32(tmem_c, da, db, idesc, acc);
+  }
+};
+constexpr float kPairLoScale = 2048.f;  // lo plane of an FP16 pair holds (x - hi) * 2^11
+
+// 2^e as a float, e in [-126, 127]
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
+// x * 2^sh for any sh in [-252, 252] without intermediate overflow of the multiplier
+__device__ __forceinline__ float scale_pow2(float x, int sh) {
+  const int s1 = max(-126, min(126, sh));
+  return x * exp2i(s1) * exp2i(sh - s1);
+}
+
 // UMMA shared-memory descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp): start address >> 4 in bits [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type
 // SWIZZLE_128B = 2 in [61,64).  K-major SW128 tile: rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1).
@@ -104,6 +140,32 @@ inline bool make_map_2d(CUtensorMap* map, const float* base, long long rows, lon
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// FP16 planes: 2-D [rows][cols] with leading dimension ld (elements, multiple of 8); SWIZZLE_128B for both majors.
+inline bool make_map_2d_f16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                            int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool make_map_nhwc_f16(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_c, int box_w,
+                              int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // 4-D NHWC fp32 activation tensor [B][H][W][C] (dense); box = {box_c, box_w, box_h, 1}.  Out-of-range coordinates

@@ -32,8 +32,11 @@ struct TcConvParams {
   const float* bias;
   int B, H, W, Cin, Cout;
   int BW, BH, tiles_x, tiles_y, BN;
+  const int* exp_x;  // FP16 pair operands: device exponents of the activation / weight planes
+  const int* exp_w;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kCvThreads, 1)
 tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -55,7 +58,9 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
   const int ty = tile % p.tiles_y;
   const int b = tile / p.tiles_y;
   const int x0 = tx * p.BW, y0 = ty * p.BH;
-  const int chunks = p.Cin / 32;
+  using E = TcElem<F16>;
+  constexpr int CK = E::kBK;  // input channels per k-block (128 bytes)
+  const int chunks = p.Cin / CK;
   const int num_kb = 9 * chunks;
   const uint32_t stage_tx = 2 * kCvTile + 2 * (uint32_t)p.BN * 128u;
 
@@ -83,15 +88,16 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
         mbar_arrive_expect_tx(&full_bar[s], stage_tx);
         const int tap = kb / chunks, cc = kb - tap * chunks;
         const int ky = tap / 3, kx = tap - ky * 3;
-        tma_load_4d(st, &map_x_hi, &full_bar[s], cc * 32, x0 + kx - 1, y0 + ky - 1, b);
-        tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * 32, x0 + kx - 1, y0 + ky - 1, b);
-        tma_load_2d(st + 2 * kCvTile, &map_w_hi, &full_bar[s], kb * 32, n0);
-        tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * 32, n0);
+        tma_load_4d(st, &map_x_hi, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
+        tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
+        tma_load_2d(st + 2 * kCvTile, &map_w_hi, &full_bar[s], kb * CK, n0);
+        tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * CK, n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc =
+          (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t tmem_lo = tmem_base + kCvHiAcc * 128;
       uint32_t accum_lo = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -106,10 +112,10 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
           const uint64_t a_lo = make_desc(st + kCvTile + ks * 32, 16u, 1024u, 2u);
           const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 32, 16u, 1024u, 2u);
           const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 32, 16u, 1024u, 2u);
-          umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+          E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
           accum_lo = 1;
-          umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_base + (uint32_t)(kb % kCvHiAcc) * 128, a_hi, b_hi, idesc, (kb >= kCvHiAcc || ks > 0) ? 1u : 0u);
+          E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+          E::mma(tmem_base + (uint32_t)(kb % kCvHiAcc) * 128, a_hi, b_hi, idesc, (kb >= kCvHiAcc || ks > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
       }
@@ -125,6 +131,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     const bool valid = (y < p.H) && (x < p.W);
     float* zrow = p.z + (((size_t)b * p.H + y) * p.W + x) * p.Cout;
     const int n_hi = min(kCvHiAcc, num_kb);
+    const int out_shift = F16 ? -(__ldg(p.exp_x) + __ldg(p.exp_w)) : 0;
     for (int cb = 0; cb < p.BN; cb += 32) {
       float acc[32];
 #pragma unroll
@@ -133,8 +140,13 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
         const int which = (a == n_hi) ? kCvHiAcc : a;
         uint32_t t[32];
         tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(which * 128 + cb), t);
+        const float w = (F16 && which == kCvHiAcc) ? 1.f / kPairLoScale : 1.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(t[j]);
+        for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(t[j]), w, acc[j]);
+      }
+      if (F16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = scale_pow2(acc[j], out_shift);
       }
       if (valid) {
 #pragma unroll
@@ -166,7 +178,9 @@ struct TcWgradParams {
   int B, H, W, Cin, Cout;
   int M, N, BN;
   int rows_per_split;  // image rows (b, y) per grid.z slice
-  int xblocks;         // ceil(W / 32)
+  int xblocks;         // ceil(W / pixels per k-block)
+  const int* exp_x;    // FP16 pair operands: device exponents of the x / dz planes
+  const int* exp_dz;
 };
 constexpr int kWgChunk = 8;  // k-blocks per TMEM accumulation chunk
 
@@ -174,6 +188,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kCvThreads, 1)
 tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                      const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
@@ -196,7 +211,11 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
   const int r_end = min(total_rows, r_begin + p.rows_per_split);
   const int num_kb = max(0, r_end - r_begin) * p.xblocks;
   const int num_chunks = (num_kb + kWgChunk - 1) / kWgChunk;
-  const int nb_boxes = p.BN / 32;
+  using E = TcElem<F16>;
+  constexpr int MB = E::kMnBox;   // channels per box (128 bytes) = rows of one (tap, channel group)
+  constexpr int PK = E::kBK;      // pixels (k rows) per k-block
+  constexpr int NGRP = 128 / MB;  // row groups of the M tile
+  const int nb_boxes = p.BN / MB;
   const uint32_t stage_tx = 2 * kCvTile + 2 * (uint32_t)p.BN * 128u;
 
   if (threadIdx.x == 0) {
@@ -220,9 +239,9 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
   if (warp == 0) {
     if (lane == 0) {
       // the four 32-row groups of this M tile: (tap, first channel) each
-      int tapj[4], cij[4];
-      for (int j = 0; j < 4; ++j) {
-        const int mrow = m0 + 32 * j;
+      int tapj[NGRP], cij[NGRP];
+      for (int j = 0; j < NGRP; ++j) {
+        const int mrow = m0 + MB * j;
         tapj[j] = (mrow < p.M) ? mrow / p.Cin : -1;
         cij[j] = (mrow < p.M) ? mrow % p.Cin : 0;
       }
@@ -235,29 +254,29 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
           mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
           unsigned char* st = smem + (size_t)s * kCvStageBytes;
           mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NGRP; ++j) {
             int cx, cy;
             if (tapj[j] >= 0) {
               const int ky = tapj[j] / 3, kx = tapj[j] - ky * 3;
-              cx = xb * 32 + kx - 1;
+              cx = xb * PK + kx - 1;
               cy = y + ky - 1;
             } else {  // rows beyond 9*Cin: a fully out-of-bounds box delivers zeros (and the expected bytes)
               cx = 0;
               cy = p.H + 4;
             }
-            tma_load_4d(st + j * 4096, &map_x_hi, &full_bar[s], cij[j], cx, cy, b);
-            tma_load_4d(st + kCvTile + j * 4096, &map_x_lo, &full_bar[s], cij[j], cx, cy, b);
+            tma_load_4d(st + j * E::kMnBoxBytes, &map_x_hi, &full_bar[s], cij[j], cx, cy, b);
+            tma_load_4d(st + kCvTile + j * E::kMnBoxBytes, &map_x_lo, &full_bar[s], cij[j], cx, cy, b);
           }
           for (int j = 0; j < nb_boxes; ++j) {
-            tma_load_4d(st + 2 * kCvTile + j * 4096, &map_dz_hi, &full_bar[s], n0 + 32 * j, xb * 32, y, b);
-            tma_load_4d(st + 3 * kCvTile + j * 4096, &map_dz_lo, &full_bar[s], n0 + 32 * j, xb * 32, y, b);
+            tma_load_4d(st + 2 * kCvTile + j * E::kMnBoxBytes, &map_dz_hi, &full_bar[s], n0 + MB * j, xb * PK, y, b);
+            tma_load_4d(st + 3 * kCvTile + j * E::kMnBoxBytes, &map_dz_lo, &full_bar[s], n0 + MB * j, xb * PK, y, b);
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+      const uint32_t idesc = (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t tmem_lo = tmem_base + kCvHiAcc * 128;
       uint32_t accum_lo = 0;
@@ -274,14 +293,15 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
           const uint32_t st = smem_u32(smem + (size_t)s * kCvStageBytes);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t a_hi = make_desc(st + ks * 1024, 4096u, 512u, 1u);
-            const uint64_t a_lo = make_desc(st + kCvTile + ks * 1024, 4096u, 512u, 1u);
-            const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 1024, 4096u, 512u, 1u);
-            const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 1024, 4096u, 512u, 1u);
-            umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+            const uint32_t off = ks * E::kMnStep;
+            const uint64_t a_hi = make_desc(st + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
+            const uint64_t a_lo = make_desc(st + kCvTile + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
+            const uint64_t b_hi = make_desc(st + 2 * kCvTile + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
+            const uint64_t b_lo = make_desc(st + 3 * kCvTile + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
+            E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
             accum_lo = 1;
-            umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
-            umma_tf32(tmem_base + (uint32_t)a * 128, a_hi, b_hi, idesc, (kb > c * kWgChunk || ks > 0) ? 1u : 0u);
+            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            E::mma(tmem_base + (uint32_t)a * 128, a_hi, b_hi, idesc, (kb > c * kWgChunk || ks > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -320,9 +340,15 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
           uint32_t t[32];
           tmem_ld32(lane_addr + (uint32_t)(kCvHiAcc * 128 + cb), t);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[cb + j] += __uint_as_float(t[j]);
+          for (int j = 0; j < 32; ++j)
+            sum[cb + j] = fmaf(__uint_as_float(t[j]), F16 ? 1.f / kPairLoScale : 1.f, sum[cb + j]);
         }
       }
+    }
+    if (F16) {
+      const int out_shift = -(__ldg(p.exp_x) + __ldg(p.exp_dz));
+#pragma unroll
+      for (int j = 0; j < 128; ++j) sum[j] = scale_pow2(sum[j], out_shift);
     }
     const int m = m0 + lane_grp * 32 + lane;
     if (m < p.M) {
@@ -416,41 +442,66 @@ static void pick_tile(int H, int W, int* BW, int* BH) {
   }
 }
 
-// z[B,H,W,Cout] = conv3x3_pad1(x) + bias on tensor cores.  x planes (hi, lo) NHWC [B,H,W,Cin], Cin % 32 == 0;
-// weight planes K-major [Cout][9*Cin] with k = (ky*3+kx)*Cin + ci; Cout % 4 == 0.
-extern "C" int vocr_tc_conv3x3_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                                   const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
-                                   vocr_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 32 == 0 && Cout % 4 == 0);
+// z[B,H,W,Cout] = conv3x3_pad1(x) + bias on tensor cores.  x planes (hi, lo) NHWC [B,H,W,Cin]; weight planes
+// K-major [Cout][9*Cin] with k = (ky*3+kx)*Cin + ci; Cout % 4 == 0.  TF32 planes: Cin % 32 == 0; FP16 pair planes
+// (vocr_split_f16_f32, with their device exponents): Cin % 64 == 0.
+template <bool F16>
+static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp_x, const void* w_hi, const void* w_lo,
+                              const int* exp_w, const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
+                              cudaStream_t stream) {
+  constexpr int CK = TcElem<F16>::kBK;
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % CK == 0 && Cout % 4 == 0);
   if (B == 0) return VOCR_OK;
-  VOCR_REQUIRE(x_hi && x_lo && w_hi && w_lo && z);
+  VOCR_REQUIRE(x_hi && x_lo && w_hi && w_lo && z && (!F16 || (exp_x && exp_w)));
   VOCR_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(z) &&
                (!bias || aligned16(bias)));
   TcConvParams p;
   p.z = z; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.exp_x = exp_x; p.exp_w = exp_w;
   pick_tile(H, W, &p.BW, &p.BH);
   p.tiles_x = ceil_div(W, p.BW);
   p.tiles_y = ceil_div(H, p.BH);
   p.BN = (Cout <= 64) ? 64 : 128;
   CUtensorMap mx_hi, mx_lo, mw_hi, mw_lo;
-  bool ok = make_map_nhwc(&mx_hi, x_hi, B, H, W, Cin, 32, p.BW, p.BH, false) &&
-            make_map_nhwc(&mx_lo, x_lo, B, H, W, Cin, 32, p.BW, p.BH, false) &&
-            make_map_2d(&mw_hi, w_hi, Cout, 9LL * Cin, 9LL * Cin, 32, p.BN) &&
-            make_map_2d(&mw_lo, w_lo, Cout, 9LL * Cin, 9LL * Cin, 32, p.BN);
+  bool ok;
+  if (F16)
+    ok = make_map_nhwc_f16(&mx_hi, x_hi, B, H, W, Cin, CK, p.BW, p.BH) &&
+         make_map_nhwc_f16(&mx_lo, x_lo, B, H, W, Cin, CK, p.BW, p.BH) &&
+         make_map_2d_f16(&mw_hi, w_hi, Cout, 9LL * Cin, 9LL * Cin, CK, p.BN) &&
+         make_map_2d_f16(&mw_lo, w_lo, Cout, 9LL * Cin, 9LL * Cin, CK, p.BN);
+  else
+    ok = make_map_nhwc(&mx_hi, static_cast<const float*>(x_hi), B, H, W, Cin, CK, p.BW, p.BH, false) &&
+         make_map_nhwc(&mx_lo, static_cast<const float*>(x_lo), B, H, W, Cin, CK, p.BW, p.BH, false) &&
+         make_map_2d(&mw_hi, static_cast<const float*>(w_hi), Cout, 9LL * Cin, 9LL * Cin, CK, p.BN) &&
+         make_map_2d(&mw_lo, static_cast<const float*>(w_lo), Cout, 9LL * Cin, 9LL * Cin, CK, p.BN);
   if (!ok) return VOCR_EXECUTION_FAILED;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_conv_fwd_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) !=
+        cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     attr_set = true;
   }
   const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
   VOCR_REQUIRE(tiles <= 2147483647LL);
   dim3 grid((unsigned)tiles, ceil_div(Cout, p.BN));
-  tc_conv_fwd_kernel<<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
+  tc_conv_fwd_kernel<F16><<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
+}
+
+extern "C" int vocr_tc_conv3x3_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                                   const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
+                                   vocr_stream_t stream_) {
+  return tc_conv_fwd_launch<false>(x_hi, x_lo, nullptr, w_hi, w_lo, nullptr, bias, z, B, H, W, Cin, Cout,
+                                   static_cast<cudaStream_t>(stream_));
+}
+extern "C" int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x,
+                                       const uint16_t* w_hi, const uint16_t* w_lo, const int32_t* exp_w,
+                                       const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
+                                       vocr_stream_t stream_) {
+  return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, z, B, H, W, Cin, Cout,
+                                  static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" size_t vocr_tc_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout) {
@@ -458,21 +509,24 @@ extern "C" size_t vocr_tc_conv3x3_wgrad_workspace_size(int B, int H, int W, int 
   return sizeof(float) * (size_t)9 * Cin * Cout * 64 + 256;
 }
 
-// dw[Cout,Cin,3,3] = sum over pixels of x(p+tap, ci) * dz(p, co); x and dz given as (hi, lo) NHWC planes,
-// Cin % 32 == 0, Cout % 32 == 0.
-extern "C" int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const float* dz_hi, const float* dz_lo,
-                                     float* dw, int B, int H, int W, int Cin, int Cout, void* workspace,
-                                     size_t workspace_bytes, vocr_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  VOCR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cin > 0 && Cout > 0);
-  VOCR_REQUIRE(x_hi && x_lo && dz_hi && dz_lo && dw && workspace);
+// dw[Cout,Cin,3,3] = sum over pixels of x(p+tap, ci) * dz(p, co); x and dz given as (hi, lo) NHWC planes.
+// TF32 planes: Cin % 32 == 0, Cout % 32 == 0; FP16 pair planes: Cin % 64 == 0, Cout % 64 == 0.
+template <bool F16>
+static int tc_conv_wgrad_launch(const void* x_hi, const void* x_lo, const int* exp_x, const void* dz_hi,
+                                const void* dz_lo, const int* exp_dz, float* dw, int B, int H, int W, int Cin,
+                                int Cout, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  using E = TcElem<F16>;
+  constexpr int MB = E::kMnBox, PK = E::kBK;
+  VOCR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % MB == 0 && Cout % MB == 0 && Cin > 0 && Cout > 0);
+  VOCR_REQUIRE(x_hi && x_lo && dz_hi && dz_lo && dw && workspace && (!F16 || (exp_x && exp_dz)));
   VOCR_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(dz_hi) && aligned16(dz_lo) && aligned16(workspace));
   TcWgradParams p;
   p.partial = static_cast<float*>(workspace);
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.M = 9 * Cin; p.N = Cout;
+  p.exp_x = exp_x; p.exp_dz = exp_dz;
   p.BN = (Cout <= 64) ? 64 : 128;
-  p.xblocks = ceil_div(W, 32);
+  p.xblocks = ceil_div(W, PK);
   const int tiles = ceil_div(p.M, 128) * ceil_div(p.N, p.BN);
   const int total_rows = B * H;
   int splits = max(1, min(64, min(total_rows, (2 * kNumSMs) / tiles)));
@@ -480,23 +534,43 @@ extern "C" int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const
   splits = ceil_div(total_rows, p.rows_per_split);
   VOCR_REQUIRE(sizeof(float) * (size_t)p.M * p.N * splits <= workspace_bytes);
   CUtensorMap mx_hi, mx_lo, md_hi, md_lo;
-  bool ok = make_map_nhwc(&mx_hi, x_hi, B, H, W, Cin, 32, 32, 1, true) &&
-            make_map_nhwc(&mx_lo, x_lo, B, H, W, Cin, 32, 32, 1, true) &&
-            make_map_nhwc(&md_hi, dz_hi, B, H, W, Cout, 32, 32, 1, true) &&
-            make_map_nhwc(&md_lo, dz_lo, B, H, W, Cout, 32, 32, 1, true);
+  bool ok;
+  if (F16)
+    ok = make_map_nhwc_f16(&mx_hi, x_hi, B, H, W, Cin, MB, PK, 1) && make_map_nhwc_f16(&mx_lo, x_lo, B, H, W, Cin, MB, PK, 1) &&
+         make_map_nhwc_f16(&md_hi, dz_hi, B, H, W, Cout, MB, PK, 1) && make_map_nhwc_f16(&md_lo, dz_lo, B, H, W, Cout, MB, PK, 1);
+  else
+    ok = make_map_nhwc(&mx_hi, static_cast<const float*>(x_hi), B, H, W, Cin, MB, PK, 1, true) &&
+         make_map_nhwc(&mx_lo, static_cast<const float*>(x_lo), B, H, W, Cin, MB, PK, 1, true) &&
+         make_map_nhwc(&md_hi, static_cast<const float*>(dz_hi), B, H, W, Cout, MB, PK, 1, true) &&
+         make_map_nhwc(&md_lo, static_cast<const float*>(dz_lo), B, H, W, Cout, MB, PK, 1, true);
   if (!ok) return VOCR_EXECUTION_FAILED;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_conv_wgrad_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) !=
+        cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     attr_set = true;
   }
   dim3 grid(ceil_div(p.N, p.BN), ceil_div(p.M, 128), splits);
-  tc_conv_wgrad_kernel<<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, md_hi, md_lo, p);
+  tc_conv_wgrad_kernel<F16><<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, md_hi, md_lo, p);
   VOCR_CHECK_LAUNCH();
   tc_wgrad_reduce_kernel<<<min(ceil_div(p.M * p.N, 256), 4 * kNumSMs), 256, 0, stream>>>(p.partial, splits, Cin, Cout, dw);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
+}
+
+extern "C" int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const float* dz_hi, const float* dz_lo,
+                                     float* dw, int B, int H, int W, int Cin, int Cout, void* workspace,
+                                     size_t workspace_bytes, vocr_stream_t stream_) {
+  return tc_conv_wgrad_launch<false>(x_hi, x_lo, nullptr, dz_hi, dz_lo, nullptr, dw, B, H, W, Cin, Cout, workspace,
+                                     workspace_bytes, static_cast<cudaStream_t>(stream_));
+}
+extern "C" int vocr_tc_conv3x3_wgrad_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x,
+                                         const uint16_t* dz_hi, const uint16_t* dz_lo, const int32_t* exp_dz, float* dw,
+                                         int B, int H, int W, int Cin, int Cout, void* workspace,
+                                         size_t workspace_bytes, vocr_stream_t stream_) {
+  return tc_conv_wgrad_launch<true>(x_hi, x_lo, exp_x, dz_hi, dz_lo, exp_dz, dw, B, H, W, Cin, Cout, workspace,
+                                    workspace_bytes, static_cast<cudaStream_t>(stream_));
 }
 
 // stats[0:C] += sum_p z[p,c], stats[C:2C] += sum_p z[p,c]^2 (float64).  C % 4 == 0, C <= 1024.

@@ -14,6 +14,8 @@
 // memory: activations [M,K], nn.Linear weights [N,K]) and MN-major (the reduction dimension is the row index: dY^T X
 // weight gradients, dY W data gradients); they differ only in the TMA box shape and the UMMA descriptor strides.
 // Every mbarrier wait is bounded and traps, so a descriptor bug surfaces as a launch error, not a hung GPU.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace vocr {
@@ -34,6 +36,8 @@ struct TcGemmParams {
   int relu, accumulate;
   int a_mn, b_mn;  // 1 = MN-major operand
   int kb_per_split;
+  const int* exp_a;  // FP16 pair operands: planes hold A * 2^exp_a[0], B * 2^exp_b[0] (device scalars)
+  const int* exp_b;
 };
 constexpr int kTcChunk = 8;  // k-blocks accumulated in TMEM before the epilogue warps drain them into fp32 registers
 
@@ -43,8 +47,9 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 
 // Short reductions (<= 96 k-blocks, no split-K): hi*hi rotates over the 3 accumulators per k-block and everything is
 // drained once at the end (measured ~20 % faster than the chunked pipeline below at K = 1024).
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       TcGemmParams p) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -58,7 +63,9 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
-  const int num_kb = (p.K + kTcBK - 1) / kTcBK;
+  using E = TcElem<F16>;
+  constexpr int BK = E::kBK;
+  const int num_kb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
@@ -88,23 +95,23 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
         unsigned char* st = smem + (size_t)s * kTcStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
-        const int k0 = kb * kTcBK;
+        const int k0 = kb * BK;
         if (!p.a_mn) {
           tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
           tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
         } else {
-          for (int j = 0; j < 4; ++j) {                                        // 4 boxes {32 m, 32 k rows}
-            tma_load_2d(st + j * 4096, &map_a_hi, &full_bar[s], m0 + 32 * j, k0);
-            tma_load_2d(st + kTcTileBytes + j * 4096, &map_a_lo, &full_bar[s], m0 + 32 * j, k0);
+          for (int j = 0; j < kTcBM / E::kMnBox; ++j) {                        // boxes {32|64 m, BK k rows}
+            tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
+            tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
           }
         }
         if (!p.b_mn) {
           tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
           tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
         } else {
-          for (int j = 0; j < 4; ++j) {
-            tma_load_2d(st + 2 * kTcTileBytes + j * 4096, &map_b_hi, &full_bar[s], n0 + 32 * j, k0);
-            tma_load_2d(st + 3 * kTcTileBytes + j * 4096, &map_b_lo, &full_bar[s], n0 + 32 * j, k0);
+          for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
+            tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
+            tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
           }
         }
       }
@@ -113,13 +120,13 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
     // ================================ MMA issuer ================================
     if (lane == 0) {
       // instruction descriptor: D = F32 (1 << 4), A/B = TF32 (2 << 7, 2 << 10), majors, N >> 3 at bit 17, M >> 4 at 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-      // per k-step (8 elements of K): K-major advances 32 B inside the swizzle row, MN-major advances one 1024-B atom
-      const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
-      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
-      const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | ((uint32_t)p.a_mn << 15) |
+                             ((uint32_t)p.b_mn << 16) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      // per k-step (32 bytes of K): K-major advances 32 B inside the swizzle row, MN-major advances its k rows
+      const uint32_t a_step = p.a_mn ? E::kMnStep : 32u, b_step = p.b_mn ? E::kMnStep : 32u;
+      const uint32_t a_lbo = p.a_mn ? E::kMnBoxBytes : 16u, b_lbo = p.b_mn ? E::kMnBoxBytes : 16u;
+      const uint32_t a_sbo = p.a_mn ? E::kMnSbo : 1024u, b_sbo = p.b_mn ? E::kMnSbo : 1024u;
+      const uint32_t a_lt = p.a_mn ? E::kMnLayout : 2u, b_lt = p.b_mn ? E::kMnLayout : 2u;
       // The tensor core truncates (RZ) when it adds into the fp32 accumulator, once per instruction, by up to an ulp
       // of the RUNNING SUM - a bias that grows linearly with K.  Keep the running sums short and well scaled: the two
       // lo products go to their own accumulator (its sum is 2^-11 smaller), hi*hi rotates over 3 accumulators by
@@ -133,16 +140,16 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
 #pragma unroll
-        for (int ks = 0; ks < kTcBK / 8; ++ks) {
+        for (int ks = 0; ks < 4; ++ks) {
           const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, a_sbo, a_lt);
           const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
           const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
           const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+          E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
           accum_lo = 1;
-          umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_base + (uint32_t)(kb % kTcHiAcc) * kTcBN, a_hi, b_hi, idesc,
-                    (kb >= kTcHiAcc || ks > 0) ? 1u : 0u);
+          E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+          E::mma(tmem_base + (uint32_t)(kb % kTcHiAcc) * kTcBN, a_hi, b_hi, idesc,
+                 (kb >= kTcHiAcc || ks > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
       }
@@ -156,7 +163,7 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
     const int m = m0 + lane_grp * 32 + lane;
     float* crow = p.c + (size_t)m * p.ldc;
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
-#pragma unroll 1
+    const int out_shift = F16 ? -(__ldg(p.exp_a) + __ldg(p.exp_b)) : 0;
     const int n_hi = min(kTcHiAcc, num_kb);  // hi accumulators that were actually written
     for (int cb = 0; cb < kTcBN; cb += 32) {
       float r[32];
@@ -177,8 +184,13 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float w = (F16 && which == kTcHiAcc) ? 1.f / kPairLoScale : 1.f;  // lo products carry the 2^11
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] += __uint_as_float(t[j]);
+        for (int j = 0; j < 32; ++j) r[j] = fmaf(__uint_as_float(t[j]), w, r[j]);
+      }
+      if (F16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = scale_pow2(r[j], out_shift);
       }
       if (m < p.M) {
 #pragma unroll
@@ -221,8 +233,9 @@ tc_gemm_tf32x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
 // So (1) the two lo products go to their own accumulator (its running sum is 2^-11 smaller), and (2) hi*hi is cut
 // into chunks of kTcChunk k-blocks (32 accumulations) that rotate over 3 TMEM accumulators; the epilogue warps drain a
 // finished chunk into fp32 registers with round-to-nearest adds while the next chunk runs on another accumulator.
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       TcGemmParams p) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -238,7 +251,9 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
-  const int total_kb = (p.K + kTcBK - 1) / kTcBK;
+  using E = TcElem<F16>;
+  constexpr int BK = E::kBK;
+  const int total_kb = (p.K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int num_kb = max(0, min(total_kb, kb_begin + p.kb_per_split) - kb_begin);
   // short reductions (<= 96 k-blocks): one chunk per accumulator, nothing is drained before the end
@@ -272,23 +287,23 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
         unsigned char* st = smem + (size_t)s * kTcStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
-        const int k0 = (kb_begin + i) * kTcBK;
+        const int k0 = (kb_begin + i) * BK;
         if (!p.a_mn) {
           tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
           tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
         } else {
-          for (int j = 0; j < 4; ++j) {                                        // 4 boxes {32 m, 32 k rows}
-            tma_load_2d(st + j * 4096, &map_a_hi, &full_bar[s], m0 + 32 * j, k0);
-            tma_load_2d(st + kTcTileBytes + j * 4096, &map_a_lo, &full_bar[s], m0 + 32 * j, k0);
+          for (int j = 0; j < kTcBM / E::kMnBox; ++j) {                        // boxes {32|64 m, BK k rows}
+            tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
+            tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
           }
         }
         if (!p.b_mn) {
           tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
           tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
         } else {
-          for (int j = 0; j < 4; ++j) {
-            tma_load_2d(st + 2 * kTcTileBytes + j * 4096, &map_b_hi, &full_bar[s], n0 + 32 * j, k0);
-            tma_load_2d(st + 3 * kTcTileBytes + j * 4096, &map_b_lo, &full_bar[s], n0 + 32 * j, k0);
+          for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
+            tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
+            tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
           }
         }
       }
@@ -297,13 +312,13 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     // ================================ MMA issuer ================================
     if (lane == 0) {
       // instruction descriptor: D = F32 (1 << 4), A/B = TF32 (2 << 7, 2 << 10), majors, N >> 3 at bit 17, M >> 4 at 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-      // per k-step (8 elements of K): K-major advances 32 B inside the swizzle row, MN-major advances one 1024-B atom
-      const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
-      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
-      const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | ((uint32_t)p.a_mn << 15) |
+                             ((uint32_t)p.b_mn << 16) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      // per k-step (32 bytes of K): K-major advances 32 B inside the swizzle row, MN-major advances its k rows
+      const uint32_t a_step = p.a_mn ? E::kMnStep : 32u, b_step = p.b_mn ? E::kMnStep : 32u;
+      const uint32_t a_lbo = p.a_mn ? E::kMnBoxBytes : 16u, b_lbo = p.b_mn ? E::kMnBoxBytes : 16u;
+      const uint32_t a_sbo = p.a_mn ? E::kMnSbo : 1024u, b_sbo = p.b_mn ? E::kMnSbo : 1024u;
+      const uint32_t a_lt = p.a_mn ? E::kMnLayout : 2u, b_lt = p.b_mn ? E::kMnLayout : 2u;
       const uint32_t tmem_lo = tmem_base + kTcHiAcc * kTcBN;
       uint32_t accum_lo = 0;
       for (int c = 0; c < num_chunks; ++c) {
@@ -318,15 +333,15 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
           tc_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
 #pragma unroll
-          for (int ks = 0; ks < kTcBK / 8; ++ks) {
+          for (int ks = 0; ks < 4; ++ks) {
             const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
             const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+            E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
             accum_lo = 1;
-            umma_tf32(tmem_lo, a_hi, b_lo, idesc, 1);
-            umma_tf32(tmem_base + (uint32_t)a * kTcBN, a_hi, b_hi, idesc, (i > c * chunk_len || ks > 0) ? 1u : 0u);
+            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            E::mma(tmem_base + (uint32_t)a * kTcBN, a_hi, b_hi, idesc, (i > c * chunk_len || ks > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
         }
@@ -363,8 +378,14 @@ tc_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         uint32_t t[32];
         tmem_ld32(lane_addr + (uint32_t)(kTcHiAcc * kTcBN + cb), t);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum[cb + j] += __uint_as_float(t[j]);
+        for (int j = 0; j < 32; ++j)
+          sum[cb + j] = fmaf(__uint_as_float(t[j]), F16 ? 1.f / kPairLoScale : 1.f, sum[cb + j]);
       }
+    }
+    if (F16) {
+      const int out_shift = -(__ldg(p.exp_a) + __ldg(p.exp_b));
+#pragma unroll
+      for (int j = 0; j < kTcBN; ++j) sum[j] = scale_pow2(sum[j], out_shift);
     }
     const int m = m0 + lane_grp * 32 + lane;
     if (m < p.M) {
@@ -452,6 +473,60 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __
   }
 }
 
+
+// ---- FP16 pair planes ------------------------------------------------------------------------------------------------
+// x * 2^e -> hi = fp16(x 2^e), lo = fp16((x 2^e - hi) * 2^11): 22 significant bits where hi is a normal FP16 number
+// and an absolute error floor of bound * 2^-50 below that (lo keeps 11 bits down to 2^-25 after scaling), i.e. a
+// 22-bit format with ~40 binades of dynamic range under the tensor's bound.  e puts the bound in [2^14, 2^15).
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n4, long long n,
+                                                     unsigned* __restrict__ out_bits) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    m = fmaxf(m, fabsf(x[i]));
+  // fmaxf drops NaNs; that is fine for a scale (a NaN element stays NaN in the planes)
+  unsigned bits = __float_as_uint(m);
+  bits = __reduce_max_sync(0xffffffffu, bits);  // non-negative floats order like their bit patterns
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(out_bits, bits);
+}
+
+__device__ __forceinline__ int pair_exponent(unsigned bound_bits) {
+  const int e_field = (int)((bound_bits >> 23) & 0xffu);  // bound < 2^(e_field - 126)
+  return max(-126, min(126, 141 - e_field));              // bound * 2^e < 2^15
+}
+
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n4,
+                 long long n, const unsigned* __restrict__ bound_bits, int* __restrict__ exp_out) {
+  const int e = pair_exponent(__ldg(bound_bits));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
+  const float sc = exp2i(e);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float a0 = v.x * sc, a1 = v.y * sc, a2 = v.z * sc, a3 = v.w * sc;
+    const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((a0 - f01.x) * kPairLoScale, (a1 - f01.y) * kPairLoScale);
+    const __half2 l23 = __floats2half2_rn((a2 - f23.x) * kPairLoScale, (a3 - f23.y) * kPairLoScale);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+    pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    reinterpret_cast<uint2*>(hi)[i] = ph;
+    reinterpret_cast<uint2*>(lo)[i] = pl;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a = x[i] * sc;
+    const __half h = __float2half_rn(a);
+    hi[i] = h;
+    lo[i] = __float2half_rn((a - __half2float(h)) * kPairLoScale);
+  }
+}
+
 }  // namespace vocr
 
 using namespace vocr;
@@ -469,46 +544,79 @@ extern "C" int vocr_split_tf32_f32(const float* x, float* hi, float* lo, long lo
   return VOCR_OK;
 }
 
+// x[n] -> FP16 pair planes of x * 2^e.  state (device, 2 x int32): [0] receives e, [1] is scratch for the absmax pass.
+// bound (device float, optional): any upper bound of max|x| known to the caller (skips the absmax pass).
+extern "C" int vocr_split_f16_f32(const float* x, long long n, const float* bound, int32_t* state, uint16_t* hi,
+                                  uint16_t* lo, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(n >= 0 && state);
+  const unsigned* bits = reinterpret_cast<const unsigned*>(bound);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(hi) & 7) |
+                   (reinterpret_cast<uintptr_t>(lo) & 7)) == 0;
+  const long long n4 = al ? n / 4 : 0;
+  const int grid = (int)min((long long)kNumSMs * 8, ceil_div64(max(1ll, n / 4), 256));
+  if (!bound) {
+    if (cudaMemsetAsync(state + 1, 0, sizeof(int32_t), stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+    if (n > 0) {
+      VOCR_REQUIRE(x);
+      absmax_kernel<<<grid, 256, 0, stream>>>(x, n4, n, reinterpret_cast<unsigned*>(state + 1));
+      VOCR_CHECK_LAUNCH();
+    }
+    bits = reinterpret_cast<const unsigned*>(state + 1);
+  }
+  VOCR_REQUIRE(n == 0 || (x && hi && lo));
+  split_f16_kernel<<<max(1, grid), 256, 0, stream>>>(x, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n4,
+                                                     n, bits, state);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
 // C[M,N] = op(A) op(B) (+bias) (+C) (relu), operands pre-split into (hi, lo) planes with identical layout.
 //   a_mn = 0: A planes are [M,K] row-major (lda)      a_mn = 1: A planes are [K,M] row-major (lda)
 //   b_mn = 0: B planes are [N,K] row-major (ldb)      b_mn = 1: B planes are [K,N] row-major (ldb)
-// lda, ldb multiples of 4, plane bases 16-B aligned.  workspace (optional, 16-B aligned): enables split-K for long
-// reductions with few output tiles; any size works (the split count adapts), M*N*16 floats is ample.
-extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_hi, const float* a_lo,
-                                   int lda, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc,
-                                   const float* bias, int relu, int accumulate, void* workspace,
-                                   size_t workspace_bytes, vocr_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// TF32 planes: lda, ldb multiples of 4; FP16 pair planes: multiples of 8; plane bases 16-B aligned.
+// workspace (optional, 16-B aligned): enables split-K for long reductions with few output tiles; any size works (the
+// split count adapts), M*N*16 floats is ample.
+template <bool F16>
+static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a_hi, const void* a_lo, int lda,
+                          const int* exp_a, const void* b_hi, const void* b_lo, int ldb, const int* exp_b, float* C,
+                          int ldc, const float* bias, int relu, int accumulate, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+  using E = TcElem<F16>;
+  constexpr int BK = E::kBK, ALIGN = F16 ? 8 : 4;
   VOCR_REQUIRE(M >= 0 && N >= 0 && K >= 1);
   if (M == 0 || N == 0) return VOCR_OK;
-  VOCR_REQUIRE(a_hi && a_lo && b_hi && b_lo && C);
-  VOCR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0);
+  VOCR_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && (!F16 || (exp_a && exp_b)));
+  VOCR_REQUIRE(lda % ALIGN == 0 && ldb % ALIGN == 0);
   VOCR_REQUIRE(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
                  reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15) == 0);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  auto map2d = [](CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int bc, int br,
+                  bool mn) {
+    if (F16) return make_map_2d_f16(m, base, rows, cols, ld, bc, br);
+    return make_map_2d(m, static_cast<const float*>(base), rows, cols, ld, bc, br, mn);
+  };
   bool ok = true;
-  if (!a_mn) {
-    ok = ok && make_map_2d(&ma_hi, a_hi, M, K, lda, kTcBK, kTcBM) && make_map_2d(&ma_lo, a_lo, M, K, lda, kTcBK, kTcBM);
-  } else {
-    ok = ok && make_map_2d(&ma_hi, a_hi, K, M, lda, 32, kTcBK, true) && make_map_2d(&ma_lo, a_lo, K, M, lda, 32, kTcBK, true);
-  }
-  if (!b_mn) {
-    ok = ok && make_map_2d(&mb_hi, b_hi, N, K, ldb, kTcBK, kTcBN) && make_map_2d(&mb_lo, b_lo, N, K, ldb, kTcBK, kTcBN);
-  } else {
-    ok = ok && make_map_2d(&mb_hi, b_hi, K, N, ldb, 32, kTcBK, true) && make_map_2d(&mb_lo, b_lo, K, N, ldb, 32, kTcBK, true);
-  }
+  if (!a_mn)
+    ok = ok && map2d(&ma_hi, a_hi, M, K, lda, BK, kTcBM, false) && map2d(&ma_lo, a_lo, M, K, lda, BK, kTcBM, false);
+  else
+    ok = ok && map2d(&ma_hi, a_hi, K, M, lda, E::kMnBox, BK, true) && map2d(&ma_lo, a_lo, K, M, lda, E::kMnBox, BK, true);
+  if (!b_mn)
+    ok = ok && map2d(&mb_hi, b_hi, N, K, ldb, BK, kTcBN, false) && map2d(&mb_lo, b_lo, N, K, ldb, BK, kTcBN, false);
+  else
+    ok = ok && map2d(&mb_hi, b_hi, K, N, ldb, E::kMnBox, BK, true) && map2d(&mb_lo, b_lo, K, N, ldb, E::kMnBox, BK, true);
   if (!ok) return VOCR_EXECUTION_FAILED;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) !=
+    if (cudaFuncSetAttribute(tc_gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) !=
             cudaSuccess ||
-        cudaFuncSetAttribute(tc_gemm_tf32x3_shortk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(tc_gemm_x3_shortk_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kTcSmemBytes) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     attr_set = true;
   }
   const int tiles = ceil_div(N, kTcBN) * ceil_div(M, kTcBM);
-  const int total_kb = ceil_div(K, kTcBK);
+  const int total_kb = ceil_div(K, BK);
   // split-K for long reductions that would otherwise leave most SMs idle (weight-gradient GEMMs)
   int splits = 1;
   if (workspace && tiles * 2 <= kNumSMs && total_kb >= 32) {
@@ -519,12 +627,12 @@ extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, cons
   int kb_per_split = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kb_per_split);
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
-                 b_mn ? 1 : 0, kb_per_split};
+                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b};
   dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
   if (splits == 1 && total_kb <= 96)
-    tc_gemm_tf32x3_shortk_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    tc_gemm_x3_shortk_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   else
-    tc_gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    tc_gemm_x3_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   VOCR_CHECK_LAUNCH();
   if (splits > 1) {
     const long long total = (long long)M * N;
@@ -533,4 +641,22 @@ extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, cons
   }
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
+}
+
+extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_hi, const float* a_lo,
+                                   int lda, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc,
+                                   const float* bias, int relu, int accumulate, void* workspace,
+                                   size_t workspace_bytes, vocr_stream_t stream_) {
+  return tc_gemm_launch<false>(a_mn, b_mn, M, N, K, a_hi, a_lo, lda, nullptr, b_hi, b_lo, ldb, nullptr, C, ldc, bias,
+                               relu, accumulate, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+// Same GEMM on FP16 pair planes (vocr_split_f16_f32): planes hold op * 2^exp[0]; the epilogue undoes both scales.
+extern "C" int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const uint16_t* a_hi,
+                                  const uint16_t* a_lo, int lda, const int32_t* exp_a, const uint16_t* b_hi,
+                                  const uint16_t* b_lo, int ldb, const int32_t* exp_b, float* C, int ldc,
+                                  const float* bias, int relu, int accumulate, void* workspace,
+                                  size_t workspace_bytes, vocr_stream_t stream_) {
+  return tc_gemm_launch<true>(a_mn, b_mn, M, N, K, a_hi, a_lo, lda, exp_a, b_hi, b_lo, ldb, exp_b, C, ldc, bias, relu,
+                              accumulate, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
 }

@@ -50,13 +50,45 @@ def split_tf32(t):
     return hi, lo
 
 
+def _off16(t, elems):
+    """Device pointer `elems` fp16 elements into t."""
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + 2 * elems)
+
+
+def split_f16(t, bound=None):
+    """(hi, lo, state) FP16 pair planes of a contiguous fp32 tensor (vocr_split_f16_f32): the planes hold
+    t * 2^state[0]; `bound` is an optional device scalar >= max|t| (skips the absmax pass).  Nothing syncs."""
+    t = _c(t)
+    hi = torch.empty(t.shape, dtype=torch.float16, device=t.device)
+    lo = torch.empty(t.shape, dtype=torch.float16, device=t.device)
+    state = torch.empty((2,), dtype=torch.int32, device=t.device)
+    st = lib().vocr_split_f16_f32(ptr(t), t.numel(), ptr(bound), ptr(state), ptr(hi), ptr(lo), stream())
+    check(st, "vocr_split_f16_f32")
+    return hi, lo, state
+
+
+def _splitk_ws(M, N, K, dev):
+    if K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) < 148:  # long reduction, few tiles: allow split-K
+        wsb = 4 * M * N * 16
+        return torch.empty((wsb,), dtype=torch.uint8, device=dev), wsb
+    return None, 0
+
+
+def tc_gemm16(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
+              c_off=0):
+    """Tensor-core GEMM on FP16 pair operands: A = (hi, lo, state), B likewise (see vocr_tc_gemm_f16x3)."""
+    ws, wsb = _splitk_ws(M, N, K, C.device)
+    st = lib().vocr_tc_gemm_f16x3(int(a_mn), int(b_mn), M, N, K, _off16(A[0], a_off), _off16(A[1], a_off), lda,
+                                  ptr(A[2]), _off16(B[0], b_off), _off16(B[1], b_off), ldb, ptr(B[2]), _off(C, c_off),
+                                  ldc, ptr(bias), int(relu), int(accumulate), ptr(ws), wsb, stream())
+    check(st, "vocr_tc_gemm_f16x3")
+
+
 def tc_gemm(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
             c_off=0):
     """Tensor-core GEMM on pre-split operands: A = (hi, lo), B = (hi, lo) (see vocr_tc_gemm_tf32x3)."""
-    ws, wsb = None, 0
-    if K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) < 148:  # long reduction, few tiles: allow split-K
-        wsb = 4 * M * N * 16
-        ws = torch.empty((wsb,), dtype=torch.uint8, device=C.device)
+    ws, wsb = _splitk_ws(M, N, K, C.device)
     st = lib().vocr_tc_gemm_tf32x3(int(a_mn), int(b_mn), M, N, K, _off(A[0], a_off), _off(A[1], a_off), lda,
                                    _off(B[0], b_off), _off(B[1], b_off), ldb, _off(C, c_off), ldc, ptr(bias),
                                    int(relu), int(accumulate), ptr(ws), wsb, stream())
@@ -69,19 +101,31 @@ import os as _os
 # library's kernels - this is an engine choice, not a fallback: shapes the TMA path cannot address, i.e. leading
 # dimensions that are not multiples of 4 floats, always go to the FFMA engine).
 USE_TC = _os.environ.get("VOCR_TC", "1") != "0"
+# Operand format of the tensor-core kernels: FP16 pairs (kind::f16, default: twice the K per instruction, half the
+# plane bytes) or TF32 planes (VOCR_F16=0, and always where the FP16 alignment rules do not hold: leading dimensions
+# that are not multiples of 8, conv channel counts that are not multiples of 64).  Same three-product compensation and
+# the same 22 significant bits either way.
+USE_F16 = USE_TC and _os.environ.get("VOCR_F16", "1") != "0"
 
 
 class Operand:
     """A GEMM operand: the fp32 tensor plus, lazily, its (hi, lo) TF32 split (shared by every GEMM that reads it)."""
 
-    def __init__(self, t, split=None):
+    def __init__(self, t, split=None, split16=None, bound=None):
         self.t = _c(t) if t is not None else None  # None: split-only operand (see _ConvBNReLU.forward)
         self._split = split
+        self._split16 = split16
+        self.bound = bound  # optional device scalar >= max|t|
 
     def split(self):
         if self._split is None:
             self._split = split_tf32(self.t)
         return self._split
+
+    def split16(self):
+        if self._split16 is None:
+            self._split16 = split_f16(self.t, self.bound)
+        return self._split16
 
 
 def mm(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, accumulate=False, a_off=0, b_off=0,
@@ -90,7 +134,10 @@ def mm(transa, transb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False, a
     operands are TMA-addressable."""
     ok = USE_TC and lda % 4 == 0 and ldb % 4 == 0 and a_off % 4 == 0 and b_off % 4 == 0 and K >= 1 and \
         A.t.data_ptr() % 16 == 0 and B.t.data_ptr() % 16 == 0
-    if ok:
+    if ok and USE_F16 and lda % 8 == 0 and ldb % 8 == 0 and a_off % 8 == 0 and b_off % 8 == 0:
+        tc_gemm16(transa, 0 if transb else 1, M, N, K, A.split16(), lda, B.split16(), ldb, C, ldc, bias=bias, relu=relu,
+                  accumulate=accumulate, a_off=a_off, b_off=b_off, c_off=c_off)
+    elif ok:
         tc_gemm(transa, 0 if transb else 1, M, N, K, A.split(), lda, B.split(), ldb, C, ldc, bias=bias, relu=relu,
                 accumulate=accumulate, a_off=a_off, b_off=b_off, c_off=c_off)
     else:
@@ -192,10 +239,34 @@ def _tc_conv_wgrad(x_s, dz_s, B, H, W, Cin, Cout):
     return dw
 
 
+def _tc_conv_fwd16(x_s, w_s, bias, B, H, W, Cin, Cout):
+    """x_s, w_s: (hi, lo, state) FP16 pair planes; x NHWC [B,H,W,Cin], w K-major [Cout, 9*Cin]."""
+    z = torch.empty((B, H, W, Cout), dtype=F32, device=x_s[0].device)
+    st = lib().vocr_tc_conv3x3_fwd_f16(ptr(x_s[0]), ptr(x_s[1]), ptr(x_s[2]), ptr(w_s[0]), ptr(w_s[1]), ptr(w_s[2]),
+                                       ptr(bias), ptr(z), B, H, W, Cin, Cout, stream())
+    check(st, "vocr_tc_conv3x3_fwd_f16")
+    return z
+
+
+def _tc_conv_wgrad16(x_s, dz_s, B, H, W, Cin, Cout):
+    dev = x_s[0].device
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
+    wsb = lib().vocr_tc_conv3x3_wgrad_workspace_size(B, H, W, Cin, Cout)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    st = lib().vocr_tc_conv3x3_wgrad_f16(ptr(x_s[0]), ptr(x_s[1]), ptr(x_s[2]), ptr(dz_s[0]), ptr(dz_s[1]),
+                                         ptr(dz_s[2]), ptr(dw), B, H, W, Cin, Cout, ptr(ws), wsb, stream())
+    check(st, "vocr_tc_conv3x3_wgrad_f16")
+    return dw
+
+
 def conv3x3(x, weight, bias, x_op=None):
     """z = conv3x3_pad1(x) + bias, NHWC; picks the tensor-core kernel when Cin % 32 == 0.  Returns (z, x_operand)."""
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
+    if USE_F16 and Cin % 64 == 0 and Cout % 4 == 0:
+        x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x)
+        wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+        return _tc_conv_fwd16(x_op.split16(), wn.split16(), bias, B, H, W, Cin, Cout), x_op
     if USE_TC and Cin % 32 == 0 and Cout % 4 == 0:
         x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x)
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
@@ -208,6 +279,10 @@ def conv3x3_dgrad(dz, weight, dz_op=None):
     """dx = conv3x3 data gradient (NHWC)."""
     B, H, W, Cout = dz.shape
     Cin = weight.shape[1]
+    if USE_F16 and Cout % 64 == 0 and Cin % 4 == 0:
+        dz_op = dz_op or Operand(dz)
+        wd = Operand(weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout))
+        return _tc_conv_fwd16(dz_op.split16(), wd.split16(), None, B, H, W, Cout, Cin), dz_op
     if USE_TC and Cout % 32 == 0 and Cin % 4 == 0:
         dz_op = dz_op or Operand(dz)
         wd = Operand(weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout))
@@ -219,6 +294,10 @@ def conv3x3_dgrad(dz, weight, dz_op=None):
 def conv3x3_wgrad(x, dz, x_op=None, dz_op=None):
     B, H, W, Cin = x.shape
     Cout = dz.shape[3]
+    if USE_F16 and Cin % 64 == 0 and Cout % 64 == 0:
+        x_op = x_op or Operand(x)
+        dz_op = dz_op or Operand(dz)
+        return _tc_conv_wgrad16(x_op.split16(), dz_op.split16(), B, H, W, Cin, Cout)
     if USE_TC and Cin % 32 == 0 and Cout % 32 == 0:
         x_op = x_op or Operand(x)
         dz_op = dz_op or Operand(dz)
@@ -262,7 +341,7 @@ class _ConvBNReLU(torch.autograd.Function):
             a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
             strides = (H * W * Cout, W * Cout, Cout)
         # the next tensor-core conv reads this activation as TF32 (hi, lo) planes: let the apply kernel write them
-        want_split = USE_TC and not seq_layout and Cout % 32 == 0
+        want_split = USE_TC and not USE_F16 and not seq_layout and Cout % 32 == 0
         a_hi = torch.empty_like(a) if want_split else None
         a_lo = torch.empty_like(a) if want_split else None
         st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), ptr(a), ptr(a_hi), ptr(a_lo), B, H, W, Cout,
@@ -287,7 +366,7 @@ class _ConvBNReLU(torch.autograd.Function):
         dbeta = torch.empty((Cout,), dtype=F32, device=dev)
         dbias = torch.empty((Cout,), dtype=F32, device=dev)
         red = torch.empty((3 * Cout,), dtype=torch.float64, device=dev)
-        want_split = USE_TC and Cout % 32 == 0 and (Cin % 32 == 0 or ctx.needs_input_grad[0])
+        want_split = USE_TC and not USE_F16 and Cout % 32 == 0 and (Cin % 32 == 0 or ctx.needs_input_grad[0])
         dz_hi = torch.empty_like(dz) if want_split else None
         dz_lo = torch.empty_like(dz) if want_split else None
         st = lib().vocr_bn_relu_bwd_f32(ptr(da), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
