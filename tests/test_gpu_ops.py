@@ -213,3 +213,16 @@ def test_clamp_adam_matches_torch(cuda):
         opt.step()
         ops.clamp_adam_step(po, grad.to(cuda), m, v, step, lr=1e-3, weight_decay=0.01, clamp=5.0)
         close(po, pr, rtol=2e-6, what="adam step %d" % step)
+
+
+@pytest.mark.parametrize("rows,cols,ld", [(1000, 64, 64), (18560, 4096, 4096), (37, 96, 100), (513, 97, 97), (5, 8, 8)])
+def test_colsum(cuda, rows, cols, ld):
+    from vistaocr_b200 import ops
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.randn(rows, ld, generator=g)
+    out = torch.full((cols,), 7.0, device=cuda)
+    ops.colsum(x.to(cuda), rows, cols, ld, out)
+    want = x[:, :cols].double().sum(0)
+    assert (out.double().cpu() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()) * (rows ** 0.5 / 8 + 1)
+    ops.colsum(x.to(cuda), rows, cols, ld, out, accumulate=True)
+    assert (out.double().cpu() - 2 * want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item()) * (rows ** 0.5 / 8 + 1)

@@ -109,6 +109,8 @@ class Profiler:
         self.calls = {}
         self.launches = 0
         self.records = []  # (name, start_event, end_event, kind, work)
+        self.arg_log = []  # integer arguments of every recorded call (when keep_args is set; tools/step_profile.py)
+        self.keep_args = getattr(self, "keep_args", False)
 
     def summary(self):
         out = {}
@@ -142,6 +144,8 @@ def _wrap(name, fn):
         e.record()
         kind, work = work_fn(args) if work_fn else ("none", 0.0)
         p.records.append((name, s, e, kind, work))
+        if p.keep_args:
+            p.arg_log.append(tuple(a for a in args if isinstance(a, int)))
         return st
 
     return call

@@ -27,6 +27,10 @@ constexpr int kCvSmemBytes = kCvStages * kCvStageBytes + 1024 + 256;
 constexpr uint32_t kCvTmemCols = 512;
 constexpr int kCvHiAcc = 3;
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 struct TcConvParams {
   float* z;
   const float* bias;
@@ -172,6 +176,167 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
   }
 }
 
+// PERSISTENT variant for short reductions (9*Cin/CK <= 24 k-blocks: Cin = 64 / 128 with FP16 pairs): one CTA per SM
+// walks over (pixel tile, channel tile) pairs with the accumulators double-buffered in TMEM (set = {hi*hi, lo products}),
+// so the epilogue of tile j overlaps the MMAs of tile j+1 and the TMA ring never drains between tiles.  With K this
+// short the one-tile-per-CTA kernel above spent about as long in prologue + epilogue as in the k loop.
+constexpr int kCvPersistMaxKb = 24;
+
+template <bool F16>
+__global__ void __launch_bounds__(kCvThreads, 1)
+tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                           const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                           TcConvParams p, int n_tiles, int num_tiles) {
+  extern __shared__ unsigned char cv_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) &
+                                                         ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kCvStages;
+  uint64_t* acc_full = bars + 2 * kCvStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  using E = TcElem<F16>;
+  constexpr int CK = E::kBK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = p.Cin / CK;
+  const int num_kb = 9 * chunks;
+  const uint32_t stage_tx = 2 * kCvTile + 2 * (uint32_t)p.BN * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCvStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kCvTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int pt = tile / n_tiles;
+        const int n0 = (tile - pt * n_tiles) * p.BN;
+        const int tx = pt % p.tiles_x;
+        pt /= p.tiles_x;
+        const int ty = pt % p.tiles_y;
+        const int b = pt / p.tiles_y;
+        const int x0 = tx * p.BW, y0 = ty * p.BH;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kCvStages;
+          const uint32_t ph = (uint32_t)(it / kCvStages) & 1u;
+          mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
+          unsigned char* st = smem + (size_t)s * kCvStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          const int tap = kb / chunks, cc = kb - tap * chunks;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          tma_load_4d(st, &map_x_hi, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
+          tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
+          tma_load_2d(st + 2 * kCvTile, &map_w_hi, &full_bar[s], kb * CK, n0);
+          tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * CK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc =
+          (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      int it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const int set = j & 1;
+        mbar_wait_or_trap(&acc_empty[set], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_hi = tmem_base + (uint32_t)set * 256, tmem_lo = tmem_hi + 128;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kCvStages;
+          const uint32_t ph = (uint32_t)(it / kCvStages) & 1u;
+          mbar_wait_or_trap(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * kCvStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = make_desc(st + ks * 32, 16u, 1024u, 2u);
+            const uint64_t a_lo = make_desc(st + kCvTile + ks * 32, 16u, 1024u, 2u);
+            const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 32, 16u, 1024u, 2u);
+            const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 32, 16u, 1024u, 2u);
+            const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
+            E::mma(tmem_lo, a_lo, b_hi, idesc, acc);
+            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            E::mma(tmem_hi, a_hi, b_hi, idesc, acc);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[set]);
+      }
+    }
+  } else {
+    const int lane_grp = warp & 3;
+    const int r = lane_grp * 32 + lane;            // row of the tile = pixel iy*BW + ix
+    const int iy = r / p.BW, ix = r - iy * p.BW;
+    const int out_shift = F16 ? -(__ldg(p.exp_x) + __ldg(p.exp_w)) : 0;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const int set = j & 1;
+      int pt = tile / n_tiles;
+      const int n0 = (tile - pt * n_tiles) * p.BN;
+      const int tx = pt % p.tiles_x;
+      pt /= p.tiles_x;
+      const int ty = pt % p.tiles_y;
+      const int b = pt / p.tiles_y;
+      const int y = ty * p.BH + iy, x = tx * p.BW + ix;
+      const bool valid = (y < p.H) && (x < p.W);
+      float* zrow = p.z + (((size_t)b * p.H + y) * p.W + x) * p.Cout;
+      mbar_wait_or_trap(&acc_full[set], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)set * 256;
+#pragma unroll 1
+      for (int cb = 0; cb < p.BN; cb += 32) {
+        uint32_t th[32], tl[32];
+        tmem_ld32(lane_addr + (uint32_t)cb, th);
+        tmem_ld32(lane_addr + (uint32_t)(128 + cb), tl);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const int n = n0 + cb + q;
+            if (n < p.Cout) {  // Cout % 4 == 0
+              float v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float a =
+                    fmaf(__uint_as_float(tl[q + u]), F16 ? 1.f / kPairLoScale : 1.f, __uint_as_float(th[q + u]));
+                v[u] = F16 ? scale_pow2(a, out_shift) : a;
+              }
+              if (p.bias) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+              }
+              *reinterpret_cast<float4*>(zrow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kCvTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 struct TcWgradParams {
   float* partial;  // [splits][M][N]
@@ -184,9 +349,6 @@ struct TcWgradParams {
 };
 constexpr int kWgChunk = 8;  // k-blocks per TMEM accumulation chunk
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <bool F16>
 __global__ void __launch_bounds__(kCvThreads, 1)
@@ -478,13 +640,23 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_conv_fwd_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) !=
-        cudaSuccess)
+            cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv_fwd_persist_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kCvSmemBytes) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     attr_set = true;
   }
   const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
-  VOCR_REQUIRE(tiles <= 2147483647LL);
-  dim3 grid((unsigned)tiles, ceil_div(Cout, p.BN));
+  const int n_tiles = ceil_div(Cout, p.BN);
+  VOCR_REQUIRE(tiles * n_tiles <= 2147483647LL);
+  if (9 * (Cin / CK) <= kCvPersistMaxKb) {
+    const int total = (int)(tiles * n_tiles);
+    tc_conv_fwd_persist_kernel<F16><<<min(total, kNumSMs), kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi,
+                                                                                                mw_lo, p, n_tiles, total);
+    VOCR_CHECK_LAUNCH();
+    return VOCR_OK;
+  }
+  dim3 grid((unsigned)tiles, n_tiles);
   tc_conv_fwd_kernel<F16><<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi, mw_lo, p);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;

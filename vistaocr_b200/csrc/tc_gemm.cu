@@ -228,6 +228,187 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 }
 
 
+// Short reductions, PERSISTENT: one CTA per SM walks over output tiles; the accumulators are double-buffered in TMEM
+// (set = {hi*hi, lo products} x 128 columns, two sets = 512 columns), so the epilogue warps drain tile j while the MMA
+// warp already runs tile j+1 and the TMA warp prefetches across tile boundaries.  With K <= 24 k-blocks (<= 96
+// accumulations into the hi accumulator) the round-toward-zero bias stays below 6e-6 relative; longer reductions use
+// the rotating / chunked kernels.  (The xproj GEMM of the LSTM layers, K = 1024, spent ~half its time in un-overlapped
+// prologues and epilogues before this.)
+constexpr int kTcPersistMaxKb = 24;
+
+template <bool F16>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                          TcGemmParams p, int tiles_n, int num_tiles) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
+                                                         ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + kTcStages;        // [stages]
+  uint64_t* acc_full = bars + 2 * kTcStages;     // [2] accumulator set complete
+  uint64_t* acc_empty = acc_full + 2;            // [2] accumulator set drained (128 epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  using E = TcElem<F16>;
+  constexpr int BK = E::kBK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int it = 0;  // k-blocks issued so far (the stage ring runs across tiles)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kTcBM, n0 = (tile % tiles_n) * kTcBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kTcStages;
+          const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
+          mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
+          unsigned char* st = smem + (size_t)s * kTcStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
+            tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
+          } else {
+            for (int j = 0; j < kTcBM / E::kMnBox; ++j) {
+              tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
+              tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
+            }
+          }
+          if (!p.b_mn) {
+            tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
+            tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          } else {
+            for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
+              tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
+              tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (E::kFmt << 7) | (E::kFmt << 10) | ((uint32_t)p.a_mn << 15) |
+                             ((uint32_t)p.b_mn << 16) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      const uint32_t a_step = p.a_mn ? E::kMnStep : 32u, b_step = p.b_mn ? E::kMnStep : 32u;
+      const uint32_t a_lbo = p.a_mn ? E::kMnBoxBytes : 16u, b_lbo = p.b_mn ? E::kMnBoxBytes : 16u;
+      const uint32_t a_sbo = p.a_mn ? E::kMnSbo : 1024u, b_sbo = p.b_mn ? E::kMnSbo : 1024u;
+      const uint32_t a_lt = p.a_mn ? E::kMnLayout : 2u, b_lt = p.b_mn ? E::kMnLayout : 2u;
+      int it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const int set = j & 1;
+        mbar_wait_or_trap(&acc_empty[set], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_hi = tmem_base + (uint32_t)set * 2 * kTcBN, tmem_lo = tmem_hi + kTcBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kTcStages;
+          const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
+          mbar_wait_or_trap(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + (size_t)s * kTcStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = make_desc(st + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
+            const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
+            const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
+            E::mma(tmem_lo, a_lo, b_hi, idesc, acc);
+            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            E::mma(tmem_hi, a_hi, b_hi, idesc, acc);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[set]);
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int lane_grp = warp & 3;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+    const int out_shift = F16 ? -(__ldg(p.exp_a) + __ldg(p.exp_b)) : 0;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const int set = j & 1;
+      const int m0 = (tile / tiles_n) * kTcBM, n0 = (tile % tiles_n) * kTcBN;
+      mbar_wait_or_trap(&acc_full[set], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const int m = m0 + lane_grp * 32 + lane;
+      float* crow = p.c + (size_t)m * p.ldc;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)set * 2 * kTcBN;
+#pragma unroll 1
+      for (int cb = 0; cb < kTcBN; cb += 32) {
+        if (n0 + cb >= p.N) break;  // warp-uniform
+        uint32_t th[32], tl[32];
+        tmem_ld32(lane_addr + (uint32_t)cb, th);
+        tmem_ld32(lane_addr + (uint32_t)(kTcBN + cb), tl);
+        float r[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float v = fmaf(__uint_as_float(tl[q]), F16 ? 1.f / kPairLoScale : 1.f, __uint_as_float(th[q]));
+          r[q] = F16 ? scale_pow2(v, out_shift) : v;
+        }
+        if (m < p.M) {
+#pragma unroll
+          for (int q0 = 0; q0 < 32; q0 += 4) {
+            const int n = n0 + cb + q0;
+            if (n >= p.N) break;
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float x = r[q0 + q];
+              if (n + q < p.N) {
+                if (p.bias) x += __ldg(p.bias + n + q);
+                if (p.accumulate) x += crow[n + q];
+                if (p.relu) x = fmaxf(x, 0.f);
+              }
+              v[q] = x;
+            }
+            if (vec && n + 3 < p.N) {
+              *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (n + q < p.N) crow[n + q] = v[q];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cta(&acc_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
 // Accumulation scheme (all K): the tensor core adds into its fp32 accumulator with round-toward-zero, once per
 // instruction, by up to an ulp of the RUNNING SUM - a bias that grows linearly with the number of accumulations.
 // So (1) the two lo products go to their own accumulator (its running sum is 2^-11 smaller), and (2) hi*hi is cut
@@ -611,6 +792,8 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
     if (cudaFuncSetAttribute(tc_gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) !=
             cudaSuccess ||
         cudaFuncSetAttribute(tc_gemm_x3_shortk_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kTcSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_x3_persist_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kTcSmemBytes) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     attr_set = true;
@@ -629,7 +812,10 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
                  b_mn ? 1 : 0, kb_per_split, exp_a, exp_b};
   dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
-  if (splits == 1 && total_kb <= 96)
+  if (splits == 1 && total_kb <= kTcPersistMaxKb)
+    tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, p, ceil_div(N, kTcBN), tiles);
+  else if (splits == 1 && total_kb <= 96)
     tc_gemm_x3_shortk_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   else
     tc_gemm_x3_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
