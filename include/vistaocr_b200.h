@@ -119,18 +119,25 @@ int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const
  *   of vocr_bn_relu_bwd_f32 likewise.
  * vocr_bn_relu_bwd_f32: da (same strided layout) -> dz[B,H,W,C], dgamma, dbeta, dbias (= sum dz, the gradient of
  *   the conv bias in front of the BatchNorm; may be NULL).  red_ws: float64[3*C] scratch.
+ * FP16 pair planes (see vocr_split_f16_f32) come out of the same kernels without an extra pass over the tensor:
+ *   vocr_bn_finalize_f32 aux (device float[2], optional): [0] = an analytic upper bound of the activations (batch
+ *     statistics only: |xhat| <= sqrt(count); 0 otherwise), [1] = max_c |scale_c|.
+ *   vocr_bn_relu_apply_f32 a_hi16 / a_lo16 / bound (= aux) / pair_exp (device int32, receives the exponent).
+ *   vocr_bn_relu_bwd_f32 dz_hi16 / dz_lo16 / scale_max (= aux + 1) / pair_state (device int32[2]: [0] receives the
+ *     exponent, [1] scratch); the bound max|scale| * max|g| * (2 + sqrt(N)) is formed on the device.
  */
 int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, float momentum, float eps, int training,
-                         float* scale, float* shift, float* save_mean, float* save_invstd, int C,
+                         float* scale, float* shift, float* save_mean, float* save_invstd, int C, float* aux,
                          vocr_stream_t stream);
 int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, float* a_hi, float* a_lo,
-                           int B, int H, int W, int C, long long sB, long long sH, long long sW,
-                           vocr_stream_t stream);
+                           int B, int H, int W, int C, long long sB, long long sH, long long sW, uint16_t* a_hi16,
+                           uint16_t* a_lo16, const float* bound, int32_t* pair_exp, vocr_stream_t stream);
 int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float* scale, const float* shift,
                          const float* save_mean, const float* save_invstd, int training, int B, int H, int W, int C,
                          long long sB, long long sH, long long sW, float* dz, float* dz_hi, float* dz_lo,
-                         float* dgamma, float* dbeta, float* dbias, double* red_ws, vocr_stream_t stream);
+                         float* dgamma, float* dbeta, float* dbias, double* red_ws, uint16_t* dz_hi16,
+                         uint16_t* dz_lo16, const float* scale_max, int32_t* pair_state, vocr_stream_t stream);
 
 /* FractionalMaxPool2d(2, output_ratio=(0.5,0.7)) with explicit per-(sample,channel) samples[B,C,2]
  * (src/models/cnnlstm.py:127,130; ATen interval rule, random in train AND eval).  idx (int32, may be NULL) keeps the

@@ -34,11 +34,12 @@ PROTOTYPES = {
     "vocr_rds_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
     "vocr_rds_unpool_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
     "vocr_rds_wgrad_c1_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
-    "vocr_bn_finalize_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_f, c_f, c_int, c_p, c_p, c_p, c_p, c_int, c_p]),
+    "vocr_bn_finalize_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_f, c_f, c_int, c_p, c_p, c_p, c_p, c_int, c_p,
+                                     c_p]),
     "vocr_bn_relu_apply_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
-                                       c_p]),
+                                       c_p, c_p, c_p, c_p, c_p]),
     "vocr_bn_relu_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll,
-                                     c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+                                     c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "vocr_fracpool_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "vocr_fracpool_bwd_f32": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "vocr_bilstm_workspace_size": (c_sz, [c_int, c_int, c_int]),

@@ -154,7 +154,8 @@ class CnnOcrModel(nn.Module):
             training = self.training and bn.training
             last = k == n_blocks - 1
             feat = ops.conv_bn_relu(feat, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
-                                    bn.running_var, training, bn.momentum, bn.eps, seq_layout=last)
+                                    bn.running_var, training, bn.momentum, bn.eps, seq_layout=last,
+                                    planes=not last and not _CONV_PLAN[k][1])
             if training:
                 bn.num_batches_tracked += 1
             if _CONV_PLAN[k][1]:

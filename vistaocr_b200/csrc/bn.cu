@@ -5,6 +5,7 @@
 // pass (masked reductions, then dz and the conv-bias gradient).  HBM-bound elementwise / reduction kernels: float4
 // along C, grids sized in multiples of the SM count.
 #include "common.cuh"
+#include "pair_f16.cuh"
 
 namespace vocr {
 
@@ -18,7 +19,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, int training,
                                    float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C,
+                                   unsigned* __restrict__ aux) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, invstd;
@@ -42,14 +44,29 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
   shift[c] = beta[c] - mean * sc;
   if (save_mean) save_mean[c] = mean;
   if (save_invstd) save_invstd[c] = invstd;
+  if (aux) {
+    // aux[0]: an upper bound of the activations relu(gamma * xhat + beta): with batch statistics |xhat| <= sqrt(count)
+    // (one value cannot exceed the whole sum of squares).  Loose by ~2^9, which the FP16 pair format absorbs
+    // (pair_f16.cuh).  Not available with running statistics (0 -> the consumer computes an absmax).
+    // aux[1]: max_c |scale_c| (bounds the backward pass's dz).  Non-negative floats order like their bit patterns.
+    if (training) atomicMax(&aux[0], __float_as_uint(fabsf(gamma[c]) * sqrtf((float)count) + fabsf(beta[c])));
+    atomicMax(&aux[1], __float_as_uint(fabsf(sc)));
+  }
 }
 
 // a[b,y,x,c] (strided) = relu(z[p,c]*scale[c] + shift[c])
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                      float* __restrict__ a, float* __restrict__ a_hi, float* __restrict__ a_lo, long long P, int H,
-                     int W, int C4, long long sB, long long sH, long long sW) {
+                     int W, int C4, long long sB, long long sH, long long sW, __half* __restrict__ a_hi16,
+                     __half* __restrict__ a_lo16, const unsigned* __restrict__ bound_bits, int* __restrict__ exp_out) {
   const long long total = P * C4;
+  float psc = 1.f;  // 2^e of the FP16 pair planes
+  if (a_hi16) {
+    const int e = pair_exponent(__ldg(bound_bits));
+    psc = exp2i(e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
+  }
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(idx % C4);
@@ -76,6 +93,12 @@ bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scal
       *reinterpret_cast<float4*>(a_hi + o) = h;
       *reinterpret_cast<float4*>(a_lo + o) = l;
     }
+    if (a_hi16) {  // FP16 pair planes (kind::f16 kernels)
+      uint2 ph, pl;
+      pair_pack4(r.x * psc, r.y * psc, r.z * psc, r.w * psc, ph, pl);
+      *reinterpret_cast<uint2*>(a_hi16 + o) = ph;
+      *reinterpret_cast<uint2*>(a_lo16 + o) = pl;
+    }
   }
 }
 
@@ -86,8 +109,9 @@ bn_relu_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict_
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int H,
                           int W, int C4, long long sB, long long sH, long long sW, long long rows_per_cta,
-                          double* __restrict__ red) {
+                          double* __restrict__ red, unsigned* __restrict__ gmax_bits) {
   extern __shared__ float s_red[];  // [rows][C4*8]
+  float gmax = 0.f;
   const int rows = 256 / C4;
   const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
   const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
@@ -108,6 +132,7 @@ bn_relu_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict_
       const float g2 = fmaf(v.z, sc.z, sh.z) > 0.f ? d.z : 0.f;
       const float g3 = fmaf(v.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
       s1[0] += g0; s1[1] += g1; s1[2] += g2; s1[3] += g3;
+      gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(g0), fabsf(g1)), fmaxf(fabsf(g2), fabsf(g3))));
       s2[0] = fmaf(g0, (v.x - mu.x) * is.x, s2[0]);
       s2[1] = fmaf(g1, (v.y - mu.y) * is.y, s2[1]);
       s2[2] = fmaf(g2, (v.z - mu.z) * is.z, s2[2]);
@@ -129,6 +154,10 @@ bn_relu_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict_
     for (int rr = 0; rr < rows; ++rr) t += (double)s_red[((size_t)rr * C4 + (c >> 2)) * 8 + which * 4 + (c & 3)];
     atomicAdd(&red[which * C + c], t);
   }
+  if (gmax_bits) {  // max |g| over the tensor: bounds dz for the FP16 pair planes of pass 2
+    const unsigned b = __reduce_max_sync(0xffffffffu, __float_as_uint(gmax));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(gmax_bits, b);
+  }
 }
 
 // Backward pass 2: dz = scale * (g - s1/N - xhat * s2/N)  (training)  or  scale * g  (eval);  also sums dz per channel
@@ -139,8 +168,20 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__
                          const float* __restrict__ invstd, const double* __restrict__ red, double inv_count,
                          int training, long long P, int H, int W, int C4, long long sB, long long sH, long long sW,
                          long long rows_per_cta, float* __restrict__ dz, float* __restrict__ dz_hi,
-                         float* __restrict__ dz_lo, double* __restrict__ red_bias) {
+                         float* __restrict__ dz_lo, double* __restrict__ red_bias, __half* __restrict__ dz_hi16,
+                         __half* __restrict__ dz_lo16, const unsigned* __restrict__ scmax_bits,
+                         int* __restrict__ state) {
   extern __shared__ float s_red[];  // [256][4]
+  float psc = 1.f;
+  if (dz_hi16) {
+    // |dz| <= max|scale| * max|g| * (2 + sqrt(N)) with batch statistics (|mean g| <= G, |mean g xhat| <= G,
+    // |xhat| <= sqrt(N)), max|scale| * max|g| with running statistics
+    const float G = __uint_as_float(*reinterpret_cast<const unsigned*>(state + 1));
+    const float bound = __uint_as_float(__ldg(scmax_bits)) * G * (training ? 2.f + sqrtf((float)P) : 1.f);
+    const int e = pair_exponent(__float_as_uint(fminf(bound, 3.0e38f)));
+    psc = exp2i(e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = e;
+  }
   const int rows = 256 / C4;
   const int c4 = threadIdx.x % C4, r = threadIdx.x / C4;
   const int C = C4 * 4;
@@ -185,6 +226,12 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__
         *(reinterpret_cast<float4*>(dz_hi) + p * C4 + c4) = h;
         *(reinterpret_cast<float4*>(dz_lo) + p * C4 + c4) = l;
       }
+      if (dz_hi16) {
+        uint2 ph, pl;
+        pair_pack4(o.x * psc, o.y * psc, o.z * psc, o.w * psc, ph, pl);
+        *(reinterpret_cast<uint2*>(dz_hi16) + p * C4 + c4) = ph;
+        *(reinterpret_cast<uint2*>(dz_lo16) + p * C4 + c4) = pl;
+      }
     }
   }
   if (red_bias) {
@@ -214,20 +261,23 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 extern "C" int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamma, const float* beta,
                                     float* running_mean, float* running_var, float momentum, float eps,
                                     int training, float* scale, float* shift, float* save_mean, float* save_invstd,
-                                    int C, vocr_stream_t stream_) {
+                                    int C, float* aux, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VOCR_REQUIRE(C > 0 && gamma && beta && scale && shift);
   VOCR_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var));
+  if (aux && cudaMemsetAsync(aux, 0, 2 * sizeof(float), stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, (double)count, gamma, beta, running_mean,
                                                            running_var, momentum, eps, training, scale, shift,
-                                                           save_mean, save_invstd, C);
+                                                           save_mean, save_invstd, C,
+                                                           reinterpret_cast<unsigned*>(aux));
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }
 
 extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, float* a_hi,
                                       float* a_lo, int B, int H, int W, int C, long long sB, long long sH,
-                                      long long sW, vocr_stream_t stream_) {
+                                      long long sW, uint16_t* a_hi16, uint16_t* a_lo16, const float* bound,
+                                      int32_t* pair_exp, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long P = (long long)B * H * W;
   if (P == 0) return VOCR_OK;
@@ -237,7 +287,10 @@ extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const 
   const long long total = P * (C / 4);
   const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
   VOCR_REQUIRE((a_hi == nullptr) == (a_lo == nullptr));
-  bn_relu_apply_kernel<<<grid, 256, 0, stream>>>(z, scale, shift, a, a_hi, a_lo, P, H, W, C / 4, sB, sH, sW);
+  VOCR_REQUIRE(a_hi16 ? (a_lo16 && bound && pair_exp) : !a_lo16);
+  bn_relu_apply_kernel<<<grid, 256, 0, stream>>>(z, scale, shift, a, a_hi, a_lo, P, H, W, C / 4, sB, sH, sW,
+                                                 reinterpret_cast<__half*>(a_hi16), reinterpret_cast<__half*>(a_lo16),
+                                                 reinterpret_cast<const unsigned*>(bound), pair_exp);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }
@@ -248,11 +301,14 @@ extern "C" int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float
                                     const float* save_mean, const float* save_invstd, int training, int B, int H,
                                     int W, int C, long long sB, long long sH, long long sW, float* dz, float* dz_hi,
                                     float* dz_lo, float* dgamma, float* dbeta, float* dbias, double* red_ws,
+                                    uint16_t* dz_hi16, uint16_t* dz_lo16, const float* scale_max, int32_t* pair_state,
                                     vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long P = (long long)B * H * W;
   VOCR_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && red_ws && dz && dgamma && dbeta);
   if (cudaMemsetAsync(red_ws, 0, sizeof(double) * 3 * C, stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+  VOCR_REQUIRE(dz_hi16 ? (dz_lo16 && scale_max && pair_state) : !dz_lo16);
+  if (dz_hi16 && cudaMemsetAsync(pair_state, 0, 2 * sizeof(int32_t), stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
   if (P > 0) {
     VOCR_REQUIRE(da && z && scale && shift && save_mean && save_invstd);
     VOCR_REQUIRE(aligned16(z) && aligned16(da) && aligned16(dz) && sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
@@ -262,11 +318,13 @@ extern "C" int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float
     rows_per_cta = max((long long)rows * 8, ceil_div64(rows_per_cta, rows) * rows);
     const int grid = (int)ceil_div64(P, rows_per_cta);
     bn_relu_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 256 * 8, stream>>>(
-        da, z, scale, shift, save_mean, save_invstd, P, H, W, C4, sB, sH, sW, rows_per_cta, red_ws);
+        da, z, scale, shift, save_mean, save_invstd, P, H, W, C4, sB, sH, sW, rows_per_cta, red_ws,
+        dz_hi16 ? reinterpret_cast<unsigned*>(pair_state + 1) : nullptr);
     VOCR_CHECK_LAUNCH();
     bn_relu_bwd_apply_kernel<<<grid, 256, sizeof(float) * 256 * 4, stream>>>(
         da, z, scale, shift, save_mean, save_invstd, red_ws, 1.0 / (double)P, training, P, H, W, C4, sB, sH, sW,
-        rows_per_cta, dz, dz_hi, dz_lo, dbias ? red_ws + 2 * C : nullptr);
+        rows_per_cta, dz, dz_hi, dz_lo, dbias ? red_ws + 2 * C : nullptr, reinterpret_cast<__half*>(dz_hi16),
+        reinterpret_cast<__half*>(dz_lo16), reinterpret_cast<const unsigned*>(scale_max), pair_state);
     VOCR_CHECK_LAUNCH();
   }
   f64_to_f32_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(red_ws, dbeta, C);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include "pair_f16.cuh"
 
 namespace vocr {
 
@@ -51,16 +52,6 @@ struct TcElem {
     else umma_tf32(tmem_c, da, db, idesc, acc);
   }
 };
-constexpr float kPairLoScale = 2048.f;  // lo plane of an FP16 pair holds (x - hi) * 2^11
-
-// 2^e as a float, e in [-126, 127]
-__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
-// x * 2^sh for any sh in [-252, 252] without intermediate overflow of the multiplier
-__device__ __forceinline__ float scale_pow2(float x, int sh) {
-  const int s1 = max(-126, min(126, sh));
-  return x * exp2i(s1) * exp2i(sh - s1);
-}
-
 // UMMA shared-memory descriptor (sm_100 format, cute/arch/mma_sm100_desc.hpp): start address >> 4 in bits [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type
 // SWIZZLE_128B = 2 in [61,64).  K-major SW128 tile: rows of 128 B, 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1).

@@ -675,11 +675,6 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
   if ((threadIdx.x & 31) == 0 && bits) atomicMax(out_bits, bits);
 }
 
-__device__ __forceinline__ int pair_exponent(unsigned bound_bits) {
-  const int e_field = (int)((bound_bits >> 23) & 0xffu);  // bound < 2^(e_field - 126)
-  return max(-126, min(126, 141 - e_field));              // bound * 2^e < 2^15
-}
-
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n4,
                  long long n, const unsigned* __restrict__ bound_bits, int* __restrict__ exp_out) {
@@ -689,14 +684,8 @@ split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* _
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-    const float a0 = v.x * sc, a1 = v.y * sc, a2 = v.z * sc, a3 = v.w * sc;
-    const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn((a0 - f01.x) * kPairLoScale, (a1 - f01.y) * kPairLoScale);
-    const __half2 l23 = __floats2half2_rn((a2 - f23.x) * kPairLoScale, (a3 - f23.y) * kPairLoScale);
     uint2 ph, pl;
-    ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-    pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+    pair_pack4(v.x * sc, v.y * sc, v.z * sc, v.w * sc, ph, pl);
     reinterpret_cast<uint2*>(hi)[i] = ph;
     reinterpret_cast<uint2*>(lo)[i] = pl;
   }

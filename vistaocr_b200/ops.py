@@ -264,7 +264,7 @@ def conv3x3(x, weight, bias, x_op=None):
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
     if USE_F16 and Cin % 64 == 0 and Cout % 4 == 0:
-        x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x)
+        x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x, bound=getattr(x, "_vocr_bound", None))
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
         return _tc_conv_fwd16(x_op.split16(), wn.split16(), bias, B, H, W, Cin, Cout), x_op
     if USE_TC and Cin % 32 == 0 and Cout % 4 == 0:
@@ -315,7 +315,8 @@ class _ConvBNReLU(torch.autograd.Function):
     seq_layout=True writes a as the time-major sequence [W, B, H*Cout] (feature = y*Cout + c)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps, seq_layout):
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps, seq_layout,
+                planes=True):
         x = _c(x)
         _lib.require_cuda(x, "x", F32)
         B, H, W, Cin = x.shape
@@ -330,9 +331,10 @@ class _ConvBNReLU(torch.autograd.Function):
         shift = torch.empty((Cout,), dtype=F32, device=dev)
         mean = torch.empty((Cout,), dtype=F32, device=dev)
         invstd = torch.empty((Cout,), dtype=F32, device=dev)
+        aux = torch.empty((2,), dtype=F32, device=dev)  # [0] activation bound, [1] max|scale| (FP16 pair planes)
         st = lib().vocr_bn_finalize_f32(ptr(stats), B * H * W, ptr(gamma), ptr(beta), ptr(running_mean),
                                         ptr(running_var), float(momentum), float(eps), int(training), ptr(scale),
-                                        ptr(shift), ptr(mean), ptr(invstd), Cout, stream())
+                                        ptr(shift), ptr(mean), ptr(invstd), Cout, ptr(aux), stream())
         check(st, "vocr_bn_finalize_f32")
         if seq_layout:
             a = torch.empty((W, B, H * Cout), dtype=F32, device=dev)
@@ -341,23 +343,32 @@ class _ConvBNReLU(torch.autograd.Function):
             a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
             strides = (H * W * Cout, W * Cout, Cout)
         # the next tensor-core conv reads this activation as TF32 (hi, lo) planes: let the apply kernel write them
-        want_split = USE_TC and not USE_F16 and not seq_layout and Cout % 32 == 0
+        want_split = USE_TC and not USE_F16 and not seq_layout and Cout % 32 == 0 and planes
         a_hi = torch.empty_like(a) if want_split else None
         a_lo = torch.empty_like(a) if want_split else None
+        # ... or as FP16 pair planes (the analytic bound of bn_finalize needs batch statistics)
+        want16 = USE_F16 and training and not seq_layout and Cout % 64 == 0 and planes
+        a_hi16 = torch.empty(a.shape, dtype=torch.float16, device=dev) if want16 else None
+        a_lo16 = torch.empty(a.shape, dtype=torch.float16, device=dev) if want16 else None
+        pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
         st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), ptr(a), ptr(a_hi), ptr(a_lo), B, H, W, Cout,
-                                          strides[0], strides[1], strides[2], stream())
+                                          strides[0], strides[1], strides[2], ptr(a_hi16), ptr(a_lo16),
+                                          ptr(aux) if want16 else None, ptr(pstate), stream())
         check(st, "vocr_bn_relu_apply_f32")
-        if want_split:
+        if want_split or want16:
             # split-only: an Operand that held `a` would form a reference cycle (a -> attribute -> a) and keep the
             # activation and both planes alive until Python's cyclic GC runs - several GB per step
-            a._vocr_op = Operand(None, (a_hi, a_lo))
-        ctx.save_for_backward(x, weight, z, scale, shift, mean, invstd)
+            a._vocr_op = Operand(None, (a_hi, a_lo) if want_split else None,
+                                 (a_hi16, a_lo16, pstate) if want16 else None)
+        if USE_F16 and training and not seq_layout:
+            a._vocr_bound = aux  # aux[0] bounds a (and anything pooled from it): lets a later split skip its absmax
+        ctx.save_for_backward(x, weight, z, scale, shift, mean, invstd, aux)
         ctx.dims = (B, H, W, Cin, Cout, strides, bool(training))
         return a
 
     @staticmethod
     def backward(ctx, da):
-        x, weight, z, scale, shift, mean, invstd = ctx.saved_tensors
+        x, weight, z, scale, shift, mean, invstd, aux = ctx.saved_tensors
         B, H, W, Cin, Cout, strides, training = ctx.dims
         dev = x.device
         da = _c(da)
@@ -369,24 +380,34 @@ class _ConvBNReLU(torch.autograd.Function):
         want_split = USE_TC and not USE_F16 and Cout % 32 == 0 and (Cin % 32 == 0 or ctx.needs_input_grad[0])
         dz_hi = torch.empty_like(dz) if want_split else None
         dz_lo = torch.empty_like(dz) if want_split else None
+        want16 = USE_F16 and Cout % 64 == 0 and (Cin % 64 == 0 or ctx.needs_input_grad[0])
+        dz_hi16 = torch.empty(dz.shape, dtype=torch.float16, device=dev) if want16 else None
+        dz_lo16 = torch.empty(dz.shape, dtype=torch.float16, device=dev) if want16 else None
+        pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
         st = lib().vocr_bn_relu_bwd_f32(ptr(da), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
                                         int(training), B, H, W, Cout, strides[0], strides[1], strides[2], ptr(dz),
                                         ptr(dz_hi), ptr(dz_lo), ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red),
+                                        ptr(dz_hi16), ptr(dz_lo16), _off(aux, 1) if want16 else None, ptr(pstate),
                                         stream())
         check(st, "vocr_bn_relu_bwd_f32")
         dx = None
-        dz_op = Operand(dz, (dz_hi, dz_lo)) if want_split else None
+        dz_op = None
+        if want_split or want16:
+            dz_op = Operand(dz, (dz_hi, dz_lo) if want_split else None,
+                            (dz_hi16, dz_lo16, pstate) if want16 else None)
         if ctx.needs_input_grad[0]:
             dx, dz_op = conv3x3_dgrad(dz, weight, dz_op)
         dw = conv3x3_wgrad(x, dz, ctx.x_op, dz_op)
         ctx.x_op = None
-        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def conv_bn_relu(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5,
-                 seq_layout=False):
+                 seq_layout=False, planes=True):
+    """planes: the consumer is another tensor-core conv, so the apply kernel also emits the operand planes (pass False
+    when a pooling layer follows - the planes would go unread)."""
     return _ConvBNReLU.apply(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps,
-                             seq_layout)
+                             seq_layout, planes)
 
 
 class _RapidDS(torch.autograd.Function):
@@ -468,7 +489,11 @@ class _FracPool(torch.autograd.Function):
 
 
 def fracpool(x, samples):
-    return _FracPool.apply(x, samples)
+    y = _FracPool.apply(x, samples)
+    bound = getattr(x, "_vocr_bound", None)
+    if bound is not None:
+        y._vocr_bound = bound  # a max-pool cannot exceed its input
+    return y
 
 
 # ---------------------------------------------------------------------------------------------------------------
