@@ -196,6 +196,11 @@ int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_
  * ---------------------------------------------------------------------------------------------------------- */
 int vocr_split_f16_f32(const float* x, long long n, const float* bound, int32_t* state, uint16_t* hi, uint16_t* lo,
                        vocr_stream_t stream);
+/* 3x3 / pad 1 patches of a narrow NHWC activation (C % 4 == 0, meant for C < 64) as FP16 pair planes
+ * cols[B*H*W][9*C], cols[p][tap*C + c] = x[p + tap][c]: the conv of such a layer and its weight gradient then run as
+ * K = 9C GEMMs on vocr_tc_gemm_f16x3 (cols W^T and cols^T dz).  bound / state as in vocr_split_f16_f32. */
+int vocr_im2col3x3_f16(const float* x, int B, int H, int W, int C, const float* bound, int32_t* state, uint16_t* hi,
+                       uint16_t* lo, vocr_stream_t stream);
 int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const uint16_t* a_hi, const uint16_t* a_lo, int lda,
                        const int32_t* exp_a, const uint16_t* b_hi, const uint16_t* b_lo, int ldb, const int32_t* exp_b,
                        float* C, int ldc, const float* bias, int relu, int accumulate, void* workspace,

@@ -65,6 +65,29 @@ def test_tc_conv_f16_pairs_scaled_operands(cuda, xs, ds):
     close(ops.conv3x3_wgrad(xo, dzo, x_op, dz_op), wr.grad, "wgrad")
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 9, 75, 16, 64), (1, 4, 5, 8, 16), (3, 30, 200, 16, 64)])
+def test_narrow_conv_as_patch_gemm(cuda, B, H, W, Cin, Cout):
+    """Cin < 64: im2col FP16 pair planes + K = 9*Cin GEMMs (forward and weight gradient)."""
+    from vistaocr_b200 import ops
+    assert ops._narrow(Cin, Cout)
+    g = torch.Generator().manual_seed(11 + W)
+    x = torch.randn(B, Cin, H, W, generator=g).relu() * 3.0
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3.0 * Cin ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    dz = torch.randn(B, Cout, H, W, generator=g) * 1e-4
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    zr = F.conv2d(xr, wr, b.double(), padding=1)
+    zr.backward(dz.double())
+    xo, wo, dzo = nhwc(x).to(cuda), w.to(cuda), nhwc(dz).to(cuda)
+    z, x_op = ops.conv3x3(xo, wo, b.to(cuda))
+    assert getattr(x_op, "cols", False)
+    close(nchw(z), zr, "fwd")
+    close(ops.conv3x3_wgrad(xo, dzo, x_op, None), wr.grad, "wgrad")
+    close(ops.conv3x3_wgrad(xo, dzo, None, None), wr.grad, "wgrad (patches rebuilt)")
+    dx, _ = ops.conv3x3_dgrad(dzo, wo)
+    close(nchw(dx), xr.grad, "dgrad")
+
+
 def test_wgrad_long_reduction_keeps_fp32_accuracy(cuda):
     """~1.2e5 pixels with a non-zero mean (the worst case for round-toward-zero accumulation)."""
     from vistaocr_b200 import ops

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "vocr_tc_gemm_tf32x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_int, c_p, c_int,
                                     c_p, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_split_f16_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_p]),
+    "vocr_im2col3x3_f16": (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
     "vocr_tc_gemm_f16x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p,
                                    c_int, c_p, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_tc_conv3x3_fwd_f16": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
@@ -75,7 +76,7 @@ KERNELS_PER_CALL = {
     "vocr_rds_unpool_f32": 1, "vocr_rds_wgrad_c1_f32": 2, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
     "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 1, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
     "vocr_clamp_adam_f32": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
-    "vocr_split_f16_f32": 2, "vocr_tc_gemm_f16x3": 1, "vocr_tc_conv3x3_fwd_f16": 1, "vocr_tc_conv3x3_wgrad_f16": 2,
+    "vocr_split_f16_f32": 2, "vocr_im2col3x3_f16": 2, "vocr_tc_gemm_f16x3": 1, "vocr_tc_conv3x3_fwd_f16": 1, "vocr_tc_conv3x3_wgrad_f16": 2,
     "vocr_tc_conv3x3_fwd": 1, "vocr_tc_conv3x3_wgrad": 2, "vocr_colstats_f32": 1, "vocr_collate_lines_f32": 2, "vocr_lm_frontend_f32": 1, "vocr_edit_distance_i32": 1,
 }
 WORK = {
@@ -84,6 +85,7 @@ WORK = {
     "vocr_split_tf32_f32": lambda a: ("byte", 12.0 * a[3]),
     "vocr_tc_gemm_f16x3": lambda a: ("flop", 2.0 * a[2] * a[3] * a[4]),
     "vocr_split_f16_f32": lambda a: ("byte", (8.0 if a[2] else 12.0) * a[1]),
+    "vocr_im2col3x3_f16": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3] * a[4] * 10.0),
     "vocr_tc_conv3x3_fwd_f16": lambda a: ("flop", 2.0 * a[8] * a[9] * a[10] * 9 * a[11] * a[12]),
     "vocr_tc_conv3x3_wgrad_f16": lambda a: ("flop", 2.0 * a[7] * a[8] * a[9] * 9 * a[10] * a[11]),
     "vocr_tc_conv3x3_fwd": lambda a: ("flop", 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]),

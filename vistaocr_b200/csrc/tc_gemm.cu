@@ -697,6 +697,38 @@ split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* _
   }
 }
 
+
+// 3x3 / pad 1 patches of a narrow NHWC activation (C < 64, e.g. the 16 channels behind the rapid-downsample block) as
+// FP16 pair planes cols[p][tap*C + c] = x[p + tap][c] * 2^e (zero outside the image).  With so few channels the
+// implicit-GEMM conv kernels would move 128-byte swizzle rows that are mostly padding; a K = 9C GEMM over these planes
+// (forward: cols W^T, weight gradient: cols^T dz) runs on the kind::f16 GEMM kernels instead.
+__global__ void __launch_bounds__(256)
+im2col3x3_f16_kernel(const float* __restrict__ x, int B, int H, int W, int C4, __half* __restrict__ hi,
+                     __half* __restrict__ lo, const unsigned* __restrict__ bound_bits, int* __restrict__ exp_out) {
+  const int e = pair_exponent(__ldg(bound_bits));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
+  const float sc = exp2i(e);
+  const long long total = (long long)B * H * W * 9 * C4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    long long r = idx / C4;
+    const int tap = (int)(r % 9);
+    r /= 9;  // pixel
+    const int xx = (int)(r % W);
+    const int yy = (int)((r / W) % H);
+    const long long b = r / ((long long)W * H);
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+      v = __ldg(reinterpret_cast<const float4*>(x) + ((b * H + sy) * W + sx) * C4 + c4);
+    uint2 ph, pl;
+    pair_pack4(v.x * sc, v.y * sc, v.z * sc, v.w * sc, ph, pl);
+    reinterpret_cast<uint2*>(hi)[idx] = ph;  // idx = (pixel * 9 + tap) * C4 + c4: the [P][9C] row-major plane
+    reinterpret_cast<uint2*>(lo)[idx] = pl;
+  }
+}
+
 }  // namespace vocr
 
 using namespace vocr;
@@ -737,6 +769,35 @@ extern "C" int vocr_split_f16_f32(const float* x, long long n, const float* boun
   VOCR_REQUIRE(n == 0 || (x && hi && lo));
   split_f16_kernel<<<max(1, grid), 256, 0, stream>>>(x, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n4,
                                                      n, bits, state);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// x [B,H,W,C] (C % 4 == 0) -> FP16 pair planes cols [B*H*W][9*C] of the 3x3 / pad 1 patches, cols[p][tap*C + c].
+// state / bound as in vocr_split_f16_f32 (the planes share x's scale).
+extern "C" int vocr_im2col3x3_f16(const float* x, int B, int H, int W, int C, const float* bound, int32_t* state,
+                                  uint16_t* hi, uint16_t* lo, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && state);
+  const long long n = (long long)B * H * W * C;
+  const unsigned* bits = reinterpret_cast<const unsigned*>(bound);
+  if (!bound) {
+    if (cudaMemsetAsync(state + 1, 0, sizeof(int32_t), stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+    if (n > 0) {
+      VOCR_REQUIRE(x && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+      const int grid = (int)min((long long)kNumSMs * 8, ceil_div64(n / 4, 256));
+      absmax_kernel<<<grid, 256, 0, stream>>>(x, n / 4, n, reinterpret_cast<unsigned*>(state + 1));
+      VOCR_CHECK_LAUNCH();
+    }
+    bits = reinterpret_cast<const unsigned*>(state + 1);
+  }
+  if (n == 0) return VOCR_OK;
+  VOCR_REQUIRE(x && hi && lo && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0);
+  const long long total = n * 9 / 4;
+  const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
+  im2col3x3_f16_kernel<<<grid, 256, 0, stream>>>(x, B, H, W, C / 4, reinterpret_cast<__half*>(hi),
+                                                 reinterpret_cast<__half*>(lo), bits, state);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }
@@ -792,7 +853,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   // split-K for long reductions that would otherwise leave most SMs idle (weight-gradient GEMMs)
   int splits = 1;
   if (workspace && tiles * 2 <= kNumSMs && total_kb >= 32) {
-    splits = min(min(16, (2 * kNumSMs) / tiles), total_kb / 16);
+    splits = min(min(64, (2 * kNumSMs) / tiles), total_kb / 16);
     while (splits > 1 && sizeof(float) * (size_t)M * N * splits > workspace_bytes) --splits;
     if (splits < 1) splits = 1;
   }

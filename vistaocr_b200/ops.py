@@ -69,8 +69,9 @@ def split_f16(t, bound=None):
 
 
 def _splitk_ws(M, N, K, dev):
-    if K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) < 148:  # long reduction, few tiles: allow split-K
-        wsb = 4 * M * N * 16
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if K >= 1024 and tiles < 148:  # long reduction, few tiles: allow split-K (the library picks the split count)
+        wsb = 4 * M * N * max(1, min(64, (2 * 148) // tiles))
         return torch.empty((wsb,), dtype=torch.uint8, device=dev), wsb
     return None, 0
 
@@ -259,10 +260,35 @@ def _tc_conv_wgrad16(x_s, dz_s, B, H, W, Cin, Cout):
     return dw
 
 
+def im2col3x3_f16(x, bound=None):
+    """FP16 pair planes [B*H*W, 9*C] of the 3x3 / pad 1 patches of a narrow NHWC activation (vocr_im2col3x3_f16)."""
+    x = _c(x)
+    B, H, W, C = x.shape
+    hi = torch.empty((B * H * W, 9 * C), dtype=torch.float16, device=x.device)
+    lo = torch.empty((B * H * W, 9 * C), dtype=torch.float16, device=x.device)
+    state = torch.empty((2,), dtype=torch.int32, device=x.device)
+    st = lib().vocr_im2col3x3_f16(ptr(x), B, H, W, C, ptr(bound), ptr(state), ptr(hi), ptr(lo), stream())
+    check(st, "vocr_im2col3x3_f16")
+    return hi, lo, state
+
+
+def _narrow(Cin, Cout):
+    """Conv layers with too few input channels for the implicit-GEMM kernels run as K = 9*Cin GEMMs over patch planes."""
+    return USE_F16 and Cin < 64 and Cin % 8 == 0 and Cout % 8 == 0
+
+
 def conv3x3(x, weight, bias, x_op=None):
     """z = conv3x3_pad1(x) + bias, NHWC; picks the tensor-core kernel when Cin % 32 == 0.  Returns (z, x_operand)."""
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
+    if _narrow(Cin, Cout):
+        if x_op is None:
+            x_op = Operand(None, split16=im2col3x3_f16(x, getattr(x, "_vocr_bound", None)))
+            x_op.cols = True
+        wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+        z = torch.empty((B, H, W, Cout), dtype=F32, device=x.device)
+        tc_gemm16(0, 0, B * H * W, Cout, 9 * Cin, x_op.split16(), 9 * Cin, wn.split16(), 9 * Cin, z, Cout, bias=bias)
+        return z, x_op
     if USE_F16 and Cin % 64 == 0 and Cout % 4 == 0:
         x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x, bound=getattr(x, "_vocr_bound", None))
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
@@ -294,6 +320,13 @@ def conv3x3_dgrad(dz, weight, dz_op=None):
 def conv3x3_wgrad(x, dz, x_op=None, dz_op=None):
     B, H, W, Cin = x.shape
     Cout = dz.shape[3]
+    if _narrow(Cin, Cout):
+        if x_op is None or not getattr(x_op, "cols", False):
+            x_op = Operand(None, split16=im2col3x3_f16(x))
+        dz_op = dz_op or Operand(dz)
+        dwt = torch.empty((9 * Cin, Cout), dtype=F32, device=x.device)  # [(ky, kx, ci), co] = cols^T dz
+        tc_gemm16(1, 1, 9 * Cin, Cout, B * H * W, x_op.split16(), 9 * Cin, dz_op.split16(), Cout, dwt, Cout)
+        return dwt.view(3, 3, Cin, Cout).permute(3, 2, 0, 1).contiguous()
     if USE_F16 and Cin % 64 == 0 and Cout % 64 == 0:
         x_op = x_op or Operand(x)
         dz_op = dz_op or Operand(dz)
