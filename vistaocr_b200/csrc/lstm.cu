@@ -46,8 +46,8 @@ struct LstmArgs {
   float* out;           // [T,B,2H]    (fwd, pre-zeroed) | dgates [T,B,2,4H] (bwd, pre-zeroed)
   float* gates;         // [T,B,2,4H] activated i,f,g,o (fwd: written if non-null; bwd: read)
   float* cst;           // [T,B,2,H]  cell state        (fwd: written if non-null; bwd: read)
-  float* xchg;          // fwd: [n_inst][2][16][Hp hi | Hp lo] fp16 | bwd: [n_inst][2][NSL cons][NSL prod][16][US]
-  unsigned* flags;      // [n_inst], zeroed before launch
+  float* xchg;          // fwd: [n_inst][2][16][Hp hi | Hp lo | pad] fp16 | bwd: [n_inst][2][NSL cons][NSL prod][16][US]
+  unsigned* flags;      // [n_inst] arrival counters, zeroed before launch
   int T, B, H, Hp, US, NSL, Tmax, NBT, gpd, n_groups;  // gpd = instance pairs per direction
 };
 
@@ -55,6 +55,14 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_release(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
@@ -179,33 +187,65 @@ __global__ void __launch_bounds__(256 + 32 * NI, 1) bilstm_fwd_kernel(LstmArgs a
         const int tile = lstm_fold(NI * pair + i, a.NBT);
         const int inst = dir * a.NBT + tile;
         const int tm = lstm_tile_tmax(a.lens, tile * kLstmBT, a.B, a.Tmax);
-        float* hx = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
+        float* hx = a.xchg + (size_t)inst * 2 * kLstmBT * ld;  // rows padded like the shared-memory tile
         unsigned* flag = a.flags + inst;
         float* hs = hbuf + (size_t)i * kLstmBT * ld;
+#ifdef VOCR_LSTM_PROF
+        long long cw_empty = 0, cw_poll = 0, cw_copy = 0, cw_written = 0, cw_red = 0;
+        unsigned cw_nfull = 0;
+#endif
         for (int k = 0; k < tm; ++k) {
           if (k > 0) {
+#ifdef VOCR_LSTM_PROF
+            const long long q0 = clock64();
+#endif
             if (k > 1) {  // hs[i] is free once the product of step k-1 has consumed it
               mbar_wait_or_trap(&empty[i], (n_empty[i] & 1u));
               ++n_empty[i];
             }
+#ifdef VOCR_LSTM_PROF
+            const long long q1 = clock64();
+#endif
             if (lane == 0) {
               poll_flag(flag, (unsigned)(a.NSL * k));
               asm volatile("fence.proxy.async;" ::: "memory");
-              mbar_arrive_expect_tx(&full[i], (uint32_t)(kLstmBT * Hp * 4));
+              mbar_arrive_expect_tx(&full[i], (uint32_t)(kLstmBT * ld * 4));
+              // ONE bulk copy for the whole tile (a bulk copy costs ~120 cycles of serial issue whatever its size)
+              bulk_g2s(hs, hx + (size_t)((k - 1) & 1) * kLstmBT * ld, (uint32_t)(kLstmBT * ld * 4), &full[i]);
             }
             __syncwarp();
-            if (lane < kLstmBT) {
-              asm volatile("fence.proxy.async;" ::: "memory");
-              bulk_g2s(hs + (size_t)lane * ld, hx + (size_t)((k - 1) & 1) * kLstmBT * Hp + (size_t)lane * Hp,
-                       (uint32_t)(Hp * 4), &full[i]);
-            }
+#ifdef VOCR_LSTM_PROF
+            const long long q2 = clock64();
+#endif
+#ifdef VOCR_LSTM_PROF
+            mbar_wait_or_trap(&full[i], cw_nfull & 1u);  // probe only: how long the 32 KB take to land
+            ++cw_nfull;
+            const long long q3 = clock64();
+            cw_empty += q1 - q0; cw_poll += q2 - q1; cw_copy += q3 - q2;
+#endif
           }
           if (k + 1 < tm) {
+#ifdef VOCR_LSTM_PROF
+            const long long q4 = clock64();
+#endif
             mbar_wait_or_trap(&written[i], (n_written[i] & 1u));
             ++n_written[i];
+#ifdef VOCR_LSTM_PROF
+            const long long q5 = clock64();
+#endif
             if (lane == 0) red_release(flag);  // release: cumulative over the stores ordered by `written`
+#ifdef VOCR_LSTM_PROF
+            __syncwarp();
+            const long long q6 = clock64();
+            cw_written += q5 - q4; cw_red += q6 - q5;
+#endif
           }
         }
+#ifdef VOCR_LSTM_PROF
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+          printf("lstm fwd comm warp %d: steps %d  wait-empty %lld  poll %lld  copy-land %lld  wait-written %lld  red.release %lld (cycles)\n",
+                 i, tm, cw_empty, cw_poll, cw_copy, cw_written, cw_red);
+#endif
         if (tm > 1) {  // drain: the last product's release of hs[i] (keeps the phase counters in step)
           mbar_wait_or_trap(&empty[i], (n_empty[i] & 1u));
           ++n_empty[i];
@@ -231,7 +271,7 @@ __global__ void __launch_bounds__(256 + 32 * NI, 1) bilstm_fwd_kernel(LstmArgs a
         const int nb = min(kLstmBT, a.B - b0[i]);
         pok[i] = (i < ni) && pb < kLstmBT && pb < nb && pu < nu;
         plen[i] = pok[i] ? min(a.lens[b0[i] + pb], a.Tmax) : 0;
-        hx[i] = a.xchg + (size_t)inst * 2 * kLstmBT * Hp;
+        hx[i] = a.xchg + (size_t)inst * 2 * kLstmBT * ld;
         c_reg[i] = 0.f;
         h_reg[i] = 0.f;
       }
@@ -328,7 +368,7 @@ __global__ void __launch_bounds__(256 + 32 * NI, 1) bilstm_fwd_kernel(LstmArgs a
           // publish first (finished samples keep publishing their last state): the release that follows `written`
           // then does not have to wait for the bulkier stores of this step's outputs below
           if (pok[i]) {
-            __half* row = reinterpret_cast<__half*>(hx[i] + (size_t)(k & 1) * kLstmBT * Hp + (size_t)pb * Hp);
+            __half* row = reinterpret_cast<__half*>(hx[i] + (size_t)(k & 1) * kLstmBT * ld + (size_t)pb * ld);
             __half hi, lo;
             split_f16(h_reg[i], hi, lo);
             row[u0 + pu] = hi;
@@ -370,6 +410,7 @@ __global__ void __launch_bounds__(256 + 32 * NI, 1) bilstm_fwd_kernel(LstmArgs a
 // Operands are FP16 (hi, lo * 2^11) pairs like the forward pass.  Gate gradients have no fixed range, so each sample
 // row of da is scaled by a power of two (exact) that puts its largest magnitude near 2^14, and the product row is
 // scaled back in fp32: the error is relative to the largest term of the row's dot products, as in fp32 itself.
+constexpr uint32_t kBulkChunk = 32768u;  // bytes per bulk copy of the backward gather
 constexpr int kBwdWtLd = 72;   // words per W^T row: 32 hi pairs | 32 lo pairs | pad (64-bit fragment loads conflict-free)
 
 template <int NTHREADS>
@@ -423,6 +464,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
 
     if (warp >= 8) {
       // ------------------------------ communication warp of instance i ------------------------------
+      // (Per-producer flags with one 1-KB bulk copy per producer as it arrives were tried and are much slower,
+      // 9.0 vs 6.1 us/step: a bulk copy costs ~120 cycles of serial issue in the TMA unit whatever its size, so the
+      // exchange uses as few, as large copies as it can.)
       const int i = warp - 8;
       if (i < ni && lane == 0) {
         const int tile = lstm_fold(kLstmNI * pair + i, a.NBT);
@@ -442,9 +486,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
           asm volatile("fence.proxy.async;" ::: "memory");
           const uint32_t bytes = (uint32_t)blk * 4u;  // multiple of 64
           mbar_arrive_expect_tx(&ready[i], bytes);
-          for (uint32_t off = 0; off < bytes; off += 8192u)
+          for (uint32_t off = 0; off < bytes; off += kBulkChunk)
             bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off,
-                     min(8192u, bytes - off), &ready[i]);
+                     min(kBulkChunk, bytes - off), &ready[i]);
         }
       }
       __syncwarp();  // reconverge before the block-wide barrier at the top of the next group
@@ -696,9 +740,13 @@ static int lstm_geometry(int B, int H, LstmArgs* a, size_t* smem, int* grid_y, b
   return VOCR_OK;
 }
 
+static size_t lstm_flag_bytes(const LstmArgs& a, bool bwd) {
+  (void)bwd;
+  return (sizeof(unsigned) * 2 * a.NBT + 255) & ~size_t(255);
+}
 static size_t lstm_xchg_bytes(const LstmArgs& a, bool bwd) {
   if (bwd) return sizeof(float) * (size_t)(2 * a.NBT) * 2 * a.NSL * ((size_t)a.NSL * kLstmBT * a.US);
-  return sizeof(float) * (size_t)(2 * a.NBT) * 2 * kLstmBT * a.Hp;
+  return sizeof(float) * (size_t)(2 * a.NBT) * 2 * kLstmBT * (a.Hp + 8);
 }
 
 extern "C" size_t vocr_bilstm_workspace_size(int B, int H, int backward) {
@@ -706,7 +754,7 @@ extern "C" size_t vocr_bilstm_workspace_size(int B, int H, int backward) {
   size_t smem;
   int gy, variant;
   if (lstm_geometry(B, H, &a, &smem, &gy, backward != 0, &variant) != VOCR_OK) return 0;
-  return 256 + ((sizeof(unsigned) * 2 * a.NBT + 255) & ~size_t(255)) + lstm_xchg_bytes(a, backward != 0);
+  return 256 + lstm_flag_bytes(a, backward != 0) + lstm_xchg_bytes(a, backward != 0);
 }
 
 static int lstm_launch(bool bwd, LstmArgs a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -715,7 +763,7 @@ static int lstm_launch(bool bwd, LstmArgs a, void* workspace, size_t workspace_b
   int st = lstm_geometry(a.B, a.H, &a, &smem, &gy, bwd, &variant);
   if (st != VOCR_OK) return st;
   uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
-  const size_t flag_bytes = (sizeof(unsigned) * 2 * a.NBT + 255) & ~size_t(255);
+  const size_t flag_bytes = lstm_flag_bytes(a, bwd);
   const size_t xchg = lstm_xchg_bytes(a, bwd);
   if ((w - reinterpret_cast<uintptr_t>(workspace)) + flag_bytes + xchg > workspace_bytes) return VOCR_INVALID_VALUE;
   a.flags = reinterpret_cast<unsigned*>(w);
