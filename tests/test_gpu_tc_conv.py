@@ -88,6 +88,18 @@ def test_narrow_conv_as_patch_gemm(cuda, B, H, W, Cin, Cout):
     close(nchw(dx), xr.grad, "dgrad")
 
 
+def test_conv_fwd_same_sign_reduction_keeps_fp32_accuracy(cuda):
+    """Worst case for the tensor core's round-toward-zero accumulation: all products positive, K = 9 * 256."""
+    from vistaocr_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, H, W, Cin, Cout = 1, 7, 150, 256, 256
+    x = torch.rand(B, Cin, H, W, generator=g) + 0.1
+    w = torch.rand(Cout, Cin, 3, 3, generator=g) + 0.1
+    zr = F.conv2d(x.double(), w.double(), None, padding=1)
+    z, _ = ops.conv3x3(nhwc(x).to(cuda), w.to(cuda), None)
+    close(nchw(z), zr, "fwd, same-sign K=2304")
+
+
 def test_wgrad_long_reduction_keeps_fp32_accuracy(cuda):
     """~1.2e5 pixels with a non-zero mean (the worst case for round-toward-zero accumulation)."""
     from vistaocr_b200 import ops
