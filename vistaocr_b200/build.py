@@ -16,6 +16,7 @@ LIBNAME = "libvistaocr_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+CFLAGS += os.environ.get("VOCR_NVCC_FLAGS", "").split()  # e.g. -DVOCR_CTC_PROF (profiling builds; use --force)
 
 
 def lib_path():
