@@ -209,24 +209,31 @@ __device__ __forceinline__ float group8_stage_row(const float* __restrict__ row,
   return m;
 }
 
+// One CTA = one utterance x a range of frames: the utterance's symbols are staged in shared memory once, so the row loop
+// has no dependent global loads besides the row itself.
 template <bool VEC>
 __global__ void __launch_bounds__(kCtcThreads)
-ctc_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, int B, int A, int rows_per_cta,
+ctc_lattice_kernel(const float* __restrict__ acts, int T, int B, int A, int frames_per_cta,
                    const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens,
                    const int32_t* __restrict__ act_lens, int Lmax, CtcWorkspace ws) {
-  extern __shared__ __align__(16) float ctc_rowbuf[];  // [32 groups][Ap]
+  extern __shared__ __align__(16) float ctc_rowbuf[];  // [G groups][Ap] | int sym[Lmax + 1]
   const int Ap = (A + 3) & ~3;
+  const int G = blockDim.x >> 3;
   const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;
   const unsigned gmask = 0xffu << (threadIdx.x & 24);
   float* rb = ctc_rowbuf + (size_t)grp * Ap;
-  const long long row0 = (long long)blockIdx.x * rows_per_cta;
-  const int rows_here = (int)min((long long)rows_per_cta, n_rows - row0);
+  int* sym = reinterpret_cast<int*>(ctc_rowbuf + (size_t)G * Ap);
+  const int b = blockIdx.x, t0 = blockIdx.y * frames_per_cta;
+  const int Tb = min(__ldg(act_lens + b), T);
+  if (t0 >= Tb) return;
+  const int L = max(0, min(__ldg(label_lens + b), Lmax));
+  const int off = ws.offsets[b];
+  for (int j = threadIdx.x; j <= L; j += blockDim.x) sym[j] = (j == 0) ? 0 : max(0, min(__ldg(labels + off + j - 1), A - 1));
+  __syncthreads();
+  const int t1 = min(Tb, t0 + frames_per_cta);
   const int Lp = lat_stride(Lmax);
-  for (int r = grp; r < rows_here; r += (int)(blockDim.x >> 3)) {
-    const long long gr = row0 + r;
-    const int t = (int)(gr / B), b = (int)(gr - (long long)t * B);
-    if (t >= __ldg(act_lens + b)) continue;  // uniform over the 8-lane group
-    float m = group8_stage_row<VEC>(acts + gr * A, rb, A, l8, [](float x) { return x; });
+  for (int t = t0 + grp; t < t1; t += G) {
+    float m = group8_stage_row<VEC>(acts + ((size_t)t * B + b) * A, rb, A, l8, [](float x) { return x; });
     m = group8_max(m, gmask);
     const float mk = m * kLog2e;
     float s = 0.f;
@@ -240,19 +247,13 @@ ctc_lattice_kernel(const float* __restrict__ acts, long long n_rows, int T, int 
     } else {
       for (int i = l8; i < A; i += 8) s += ex2_fast(fmaf(rb[i], kLog2e, -mk));
     }
-    s = group8_sum(s, gmask);  // (also orders the buffer writes of the group before the gathers below)
+    s = group8_sum(s, gmask);
     const float lse = m + kLn2f * __log2f(s);
     const size_t bt = (size_t)b * T + t;
     if (l8 == 0) ws.lse[bt] = lse;
-    const int L = max(0, min(__ldg(label_lens + b), Lmax));
-    const int off = ws.offsets[b];
     float* lat = ws.lat + bt * (size_t)Lp;
-    __syncwarp(gmask);
-    for (int j = l8; j <= L; j += 8) {
-      int sym = (j == 0) ? 0 : __ldg(labels + off + j - 1);
-      sym = max(0, min(sym, A - 1));
-      lat[j] = (rb[sym] - lse) * kLog2e;
-    }
+    __syncwarp(gmask);  // the whole row is in the buffer
+    for (int j = l8; j <= L; j += 8) lat[j] = (rb[sym[j]] - lse) * kLog2e;
     __syncwarp(gmask);  // gathers done before the next row overwrites the buffer
   }
 }
@@ -798,26 +799,49 @@ ctc_mitm_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ 
   }
 }
 
-// ---- 4. gradient from the occupancies: 8 lanes per row ----------------------------------------------------------------
+// ---- 4. gradient from the occupancies: 8 lanes per row, one CTA = one utterance x a range of frames ------------------------
+// The utterance's symbols, duplicate chains and occupancy slots are staged in shared memory once; per row the acts and the
+// occupancy row are requested together, and the duplicate-symbol chains are walked in shared memory.
 template <bool VEC>
-__global__ void __launch_bounds__(kCtcThreads)
-ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, long long n_rows, int T, int B, int A,
-                int rows_per_cta, const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens,
+__global__ void __launch_bounds__(kCtcThreads, 4)
+ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, int T, int B, int A, int frames_per_cta,
+                const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens,
                 const int32_t* __restrict__ act_lens, int Lmax, int Q, CtcWorkspace ws) {
-  extern __shared__ __align__(16) float ctc_rowbuf[];  // [32 groups][Ap]
+  extern __shared__ __align__(16) float ctc_rowbuf[];  // [G][Ap] | occupancy rows [G][OS] | int sym, first, nxt, slotA, slotB [Lmax]
   const int Ap = (A + 3) & ~3;
+  const int OS = 32 * Q + 4;
+  const int G = blockDim.x >> 3;
   const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;
   const unsigned gmask = 0xffu << (threadIdx.x & 24);
   float* rb = ctc_rowbuf + (size_t)grp * Ap;
-  const long long row0 = (long long)blockIdx.x * rows_per_cta;
-  const int rows_here = (int)min((long long)rows_per_cta, n_rows - row0);
-  const int OS = 32 * Q + 4;
-  for (int r = grp; r < rows_here; r += (int)(blockDim.x >> 3)) {
-    const long long gr = row0 + r;
-    const int t = (int)(gr / B), b = (int)(gr - (long long)t * B);
-    float* grow = grads + gr * A;
-    const int Tb = __ldg(act_lens + b);
-    if (t >= Tb || ws.ll[b] == -INFINITY) {  // uniform over the 8-lane group
+  float* oc = ctc_rowbuf + (size_t)G * Ap + (size_t)grp * OS;
+  int* sym = reinterpret_cast<int*>(ctc_rowbuf + (size_t)G * (Ap + OS));
+  int* first = sym + Lmax;
+  int* nxt = first + Lmax;
+  int* slotA = nxt + Lmax;
+  int* slotB = slotA + Lmax;
+  const int b = blockIdx.x, t0 = blockIdx.y * frames_per_cta;
+  const int t_end = min(T, t0 + frames_per_cta);
+  const int Tb = min(__ldg(act_lens + b), T);
+  const bool feasible = ws.ll[b] != -INFINITY;
+  const int t1 = feasible ? min(Tb, t_end) : t0;  // frames [t1, t_end) are written as zeros
+  const int L = max(0, min(__ldg(label_lens + b), Lmax));
+  if (t0 < t1) {
+    const int off = ws.offsets[b];
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+      sym[j] = max(0, min(__ldg(labels + off + j), A - 1));
+      first[j] = ws.first[off + j];
+      nxt[j] = ws.nxt[off + j];
+      const int jr = L - 1 - j;
+      slotA[j] = (j % Q) * 32 + j / Q;     // position j as written by the alpha warp (frames >= Tb/2)
+      slotB[j] = (jr % Q) * 32 + jr / Q;   // ... by the beta warp, whose position order is reversed
+    }
+    __syncthreads();
+  }
+  const int mid = Tb >> 1;
+  for (int t = t0 + grp; t < t_end; t += G) {
+    float* grow = grads + ((size_t)t * B + b) * A;
+    if (t >= t1) {  // uniform over the 8-lane group
       if (VEC) {
         for (int i = l8; i < (A >> 2); i += 8) stg_stream_f4(reinterpret_cast<float4*>(grow) + i, make_float4(0.f, 0.f, 0.f, 0.f));
       } else {
@@ -826,26 +850,29 @@ ctc_grad_kernel(const float* __restrict__ acts, float* __restrict__ grads, long 
       continue;
     }
     const size_t bt = (size_t)b * T + t;
+    // request the occupancy row (asynchronous 16-byte copies straight into shared memory) and the log-sum-exp before
+    // touching the acts: all of this row's loads are in flight together
+    {
+      const float4* occ4 = reinterpret_cast<const float4*>(ws.occ + bt * (size_t)OS);
+      const uint32_t dst = smem_u32(oc);
+      for (int i = l8; i < (OS >> 2); i += 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(occ4 + i) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const float nl2 = -ws.lse[bt] * kLog2e;
-    group8_stage_row<VEC>(acts + gr * A, rb, A, l8, [nl2](float x) { return ex2_fast(fmaf(x, kLog2e, nl2)); });
+    group8_stage_row<VEC>(acts + ((size_t)t * B + b) * A, rb, A, l8, [nl2](float x) { return ex2_fast(fmaf(x, kLog2e, nl2)); });
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp(gmask);
-    const int L = max(0, min(__ldg(label_lens + b), Lmax));
-    const int off = ws.offsets[b];
-    const bool alpha_order = t >= (min(Tb, T) >> 1);  // which warp of ctc_mitm_kernel wrote this frame's occupancies
-    const float* occ = ws.occ + bt * (size_t)OS;
+    const int* slot = (t >= mid) ? slotA : slotB;
     for (int jo = l8; jo < L; jo += 8) {
-      if (ws.first[off + jo]) {
+      if (first[jo]) {
         float tot = 0.f;
-        for (int q = jo; q >= 0; q = ws.nxt[off + q]) {
-          const int j = alpha_order ? q : L - 1 - q;
-          tot += occ[(j % Q) * 32 + j / Q];
-        }
-        const int sym = max(0, min(__ldg(labels + off + jo), A - 1));
-        rb[sym] -= tot;
+        for (int q = jo; q >= 0; q = nxt[q]) tot += oc[slot[q]];
+        rb[sym[jo]] -= tot;
       }
     }
     __syncwarp(gmask);
-    if (l8 == 0) rb[0] -= occ[32 * Q];
+    if (l8 == 0) rb[0] -= oc[32 * Q];
     __syncwarp(gmask);
     if (VEC) {
       const float4* rb4 = reinterpret_cast<const float4*>(rb);
@@ -973,18 +1000,22 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
   ctc_scan_kernel<<<1, min(1024, ((B + 31) / 32) * 32), 0, stream>>>(label_lens, B, Lmax, ws);
   VOCR_CHECK_LAUNCH();
 
-  // streaming passes: 8 lanes per row, G row groups per CTA (32 unless the alphabet is very large), 4 rows per group
+  // streaming passes: 8 lanes per row, G row groups per CTA (32 unless the alphabet is very large), one CTA = one
+  // utterance x 2G frames
   const long long n_rows = (long long)T * B;
   const int Ap = (A + 3) & ~3;
+  const int Q = mitm_q(Lmax);
+  const int OSq = (Q <= kMitmMaxQ) ? 32 * Q + 4 : 0;
   int G = 32;
-  while (G > 1 && (size_t)G * Ap * 4 > 64 * 1024) G >>= 1;
-  const size_t smem_rows = (size_t)G * Ap * 4;
-  VOCR_REQUIRE(smem_rows <= 200 * 1024);
-  const int rows_per_cta = 4 * G;
-  const long long n_ctas = ceil_div64(n_rows, rows_per_cta);
-  VOCR_REQUIRE(n_ctas < (1ll << 31));
+  while (G > 1 && (size_t)G * (Ap + OSq) * 4 > 64 * 1024) G >>= 1;
+  const size_t smem_k1 = (size_t)G * Ap * 4 + sizeof(int) * (size_t)(Lmax + 1);
+  const size_t smem_k3 = (size_t)G * (Ap + OSq) * 4 + sizeof(int) * (size_t)5 * Lmax + 16;
+  VOCR_REQUIRE(smem_k1 <= 200 * 1024 && smem_k3 <= 200 * 1024);
+  const int frames_per_cta = 2 * G;
   const bool vec = (A % 4 == 0) && (reinterpret_cast<uintptr_t>(acts) % 16 == 0) &&
                    (grads == nullptr || reinterpret_cast<uintptr_t>(grads) % 16 == 0);
+  const dim3 grid_rows((unsigned)B, (unsigned)ceil_div(max(T, 1), frames_per_cta));
+  VOCR_REQUIRE(grid_rows.y <= 65535u);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(ctc_lattice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
@@ -996,14 +1027,13 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
   }
   if (n_rows > 0) {
     if (vec)
-      ctc_lattice_kernel<true><<<(unsigned)n_ctas, 8 * G, smem_rows, stream>>>(acts, n_rows, T, B, A, rows_per_cta, labels_safe,
-                                                                            label_lens, act_lens, Lmax, ws);
+      ctc_lattice_kernel<true><<<grid_rows, 8 * G, smem_k1, stream>>>(acts, T, B, A, frames_per_cta, labels_safe, label_lens,
+                                                                      act_lens, Lmax, ws);
     else
-      ctc_lattice_kernel<false><<<(unsigned)n_ctas, 8 * G, smem_rows, stream>>>(acts, n_rows, T, B, A, rows_per_cta, labels_safe,
-                                                                             label_lens, act_lens, Lmax, ws);
+      ctc_lattice_kernel<false><<<grid_rows, 8 * G, smem_k1, stream>>>(acts, T, B, A, frames_per_cta, labels_safe, label_lens,
+                                                                       act_lens, Lmax, ws);
     VOCR_CHECK_LAUNCH();
   }
-  const int Q = mitm_q(Lmax);
   if (Q <= kMitmMaxQ) {
     int st = VOCR_INVALID_VALUE;
     switch (Q) {
@@ -1017,11 +1047,11 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
     if (st != VOCR_OK) return st;
     if (grads && n_rows > 0) {
       if (vec)
-        ctc_grad_kernel<true><<<(unsigned)n_ctas, 8 * G, smem_rows, stream>>>(acts, grads, n_rows, T, B, A, rows_per_cta,
-                                                                           labels_safe, label_lens, act_lens, Lmax, Q, ws);
+        ctc_grad_kernel<true><<<grid_rows, 8 * G, smem_k3, stream>>>(acts, grads, T, B, A, frames_per_cta, labels_safe,
+                                                                     label_lens, act_lens, Lmax, Q, ws);
       else
-        ctc_grad_kernel<false><<<(unsigned)n_ctas, 8 * G, smem_rows, stream>>>(acts, grads, n_rows, T, B, A, rows_per_cta,
-                                                                            labels_safe, label_lens, act_lens, Lmax, Q, ws);
+        ctc_grad_kernel<false><<<grid_rows, 8 * G, smem_k3, stream>>>(acts, grads, T, B, A, frames_per_cta, labels_safe,
+                                                                      label_lens, act_lens, Lmax, Q, ws);
       VOCR_CHECK_LAUNCH();
     }
     return VOCR_OK;
