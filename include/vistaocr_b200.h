@@ -243,6 +243,23 @@ int vocr_collate_lines_f32(const float* packed, const long long* img_offsets, co
                            int32_t* label_lens_out, vocr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Line-image pre-processing.  Replaces, for a batch of raw decoded uint8 line images, the chain
+ * [ConvertGray] -> Scale(new_h=H) -> [InvertBlackWhite] -> ToTensor (src/imagetransforms.py:411-416,453-507,383-385,
+ * 423-434; assembled in src/decode_testset.py:48-65 and src/train_cnn_lstm.py:263-279), the 15-px width floor padded
+ * with ones (src/ocr_dataset.py:174-180) and the zero-padded, ordered batch of SortByWidthCollater
+ * (src/datautils.py:61-176).  Scale is bit-exact with what the reference's cv2.resize call computes: OpenCV's 8-bit
+ * INTER_LINEAR (the reference's INTER_CUBIC argument lands on cv2.resize's `dst` parameter), incl. the INTER_AREA
+ * re-route of exact 2x down-scaling.
+ *   packed: images back to back, uint8, gray (channels = 1) or BGR interleaved (channels = 3, converted to gray);
+ *   img_offsets [B] byte offsets;  src_h, src_w [B];  dst_w [B] = int(w * float(H / h)) from the caller (float64);
+ *   order [B] batch position -> image index, or NULL;  out [B,1,H,Wout] fp32: resized / inverted / 255 in columns
+ *   [0, dst_w), ones in [dst_w, max(dst_w, min_width)), zeros beyond.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vocr_scale_lines_u8(const uint8_t* packed, const long long* img_offsets, const int32_t* src_h,
+                        const int32_t* src_w, const int32_t* dst_w, const int32_t* order, int B, int channels, int H,
+                        int Wout, int invert, int min_width, float* out, vocr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * LM-decode front end.  Replaces the host part of LmDecoder.decode (src/decoder.py:61-101):
  * log_softmax over the alphabet, remap of model symbols to LM units (inv[u] = model index of unit u or -1, missing
  * units get `fill` = log(1e-10)), sliced per line to its valid frames, float64.  out [sum_b lens[b], U],

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "vocr_lm_frontend_f32": (c_int, [c_p, c_int, c_int, c_int, c_p, c_p, c_p, c_int, ctypes.c_double, c_p, c_p]),
     "vocr_edit_distance_i32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     "vocr_collate_lines_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "vocr_scale_lines_u8": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     "vocr_tc_gemm_tf32x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_int, c_p, c_int,
                                     c_p, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_split_f16_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_p]),
@@ -77,7 +78,7 @@ KERNELS_PER_CALL = {
     "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 1, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
     "vocr_clamp_adam_f32": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
     "vocr_split_f16_f32": 2, "vocr_im2col3x3_f16": 2, "vocr_tc_gemm_f16x3": 1, "vocr_tc_conv3x3_fwd_f16": 1, "vocr_tc_conv3x3_wgrad_f16": 2,
-    "vocr_tc_conv3x3_fwd": 1, "vocr_tc_conv3x3_wgrad": 2, "vocr_colstats_f32": 1, "vocr_collate_lines_f32": 2, "vocr_lm_frontend_f32": 1, "vocr_edit_distance_i32": 1,
+    "vocr_tc_conv3x3_fwd": 1, "vocr_tc_conv3x3_wgrad": 2, "vocr_colstats_f32": 1, "vocr_collate_lines_f32": 2, "vocr_scale_lines_u8": 1, "vocr_lm_frontend_f32": 1, "vocr_edit_distance_i32": 1,
 }
 WORK = {
     "vocr_gemm_f32": lambda a: ("flop", 2.0 * a[2] * a[3] * a[4]),
