@@ -38,7 +38,7 @@ def time_it(fn, iters=10, warmup=3, flush=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="decode,ctc")
+    ap.add_argument("--what", default="decode,ctc,preproc")
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -68,6 +68,33 @@ def main():
             print(json.dumps({"kernel": "ctc_fwd_bwd", "T": T, "B": B, "A": A, "L": L, "ms": med * 1e3,
                               "best_ms": best * 1e3, "GBs": byt / med / 1e9, "frac_hbm": byt / med / 1e9 / peak,
                               "peak": how}), flush=True)
+    if "preproc" in args.what:
+        from vistaocr_b200.imagetransforms import scaled_width  # noqa: E402
+        from vistaocr_b200 import _lib  # noqa: E402
+        rng = np.random.default_rng(9)
+        for (h, H, B, wlo, whi) in [(90, 30, 512, 600, 2400), (120, 60, 256, 800, 2400), (180, 120, 128, 600, 3000)]:
+            ws_ = rng.integers(wlo, whi + 1, size=B).astype(np.int32)
+            hs_ = np.full(B, h, np.int32)
+            dws = np.array([scaled_width(h, int(w), H) for w in ws_], np.int32)
+            offs = np.zeros(B, np.int64)
+            offs[1:] = np.cumsum(hs_[:-1].astype(np.int64) * ws_[:-1])
+            n_in = int((hs_.astype(np.int64) * ws_).sum())
+            d_pix = torch.randint(0, 256, (n_in,), dtype=torch.uint8, device=dev)
+            d_meta = torch.from_numpy(np.concatenate([hs_, ws_, dws])).to(dev)
+            d_offs = torch.from_numpy(offs).to(dev)
+            w_out = int(dws.max())
+            out = torch.empty((B, 1, H, w_out), dtype=torch.float32, device=dev)
+            l = _lib.lib()
+
+            def run():
+                _lib.check(l.vocr_scale_lines_u8(_lib.ptr(d_pix), _lib.ptr(d_offs), _lib.ptr(d_meta[0:B]),
+                                                 _lib.ptr(d_meta[B:2 * B]), _lib.ptr(d_meta[2 * B:3 * B]), None, B, 1, H,
+                                                 w_out, 1, 15, _lib.ptr(out), _lib.stream()), "scale")
+            med, best = time_it(run, args.iters, flush=flush)
+            byt = n_in + out.numel() * 4
+            print(json.dumps({"kernel": "scale_lines_u8", "h": h, "H": H, "B": B, "Wout": w_out, "ms": med * 1e3,
+                              "best_ms": best * 1e3, "GBs": byt / med / 1e9, "frac_hbm": byt / med / 1e9 / peak,
+                              "peak": how, "lines_per_s": B / med}), flush=True)
 
 
 if __name__ == "__main__":
