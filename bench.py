@@ -383,6 +383,15 @@ def side_metrics(dev, model, alphabet, pk):
     dt = (time.perf_counter() - t0) / n
     res["greedy_decode_e2e_cfg1"] = {"lines_per_s": 64 / dt, "ms_per_batch": dt * 1e3,
                                      "what": "H2D + eval forward + greedy decode to strings, 64 lines, host wall clock"}
+    del m1
+    # cfg5: mixed-width lines (reference bucket mix) in width-bucketed batches of 256 (tools/decode_bench.py; at N GPUs
+    # the lines are sharded by bucket with no collective: python -m torch.distributed.run ... tools/decode_bench.py)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    import decode_bench
+    n, dt = decode_bench.run(4096, 256, dev)
+    res["greedy_decode_e2e_cfg5"] = {"lines_per_s": n / dt, "lines": n, "batch": 256,
+                                     "what": "H2D + eval forward + greedy decode to strings, width-bucketed batches of "
+                                             "256 mixed-width lines, host wall clock, 1 GPU"}
     return res
 
 

@@ -226,3 +226,21 @@ def test_colsum(cuda, rows, cols, ld):
     assert (out.double().cpu() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item()) * (rows ** 0.5 / 8 + 1)
     ops.colsum(x.to(cuda), rows, cols, ld, out, accumulate=True)
     assert (out.double().cpu() - 2 * want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item()) * (rows ** 0.5 / 8 + 1)
+
+
+def test_first_conv_with_more_than_65535_pixel_tiles(cuda):
+    """Large decode batches (cfg5: 512 lines x 30 x 1200 px) give the Cin = 1 convolution > 65535 pixel tiles: the tile
+    index must live in grid.x.  Checked on the last image (a convolution is local to its image)."""
+    from vistaocr_b200 import ops
+    B, H, W, Cout = 40, 30, 7100, 8  # 8.52 M pixels = 66563 tiles of 128
+    g = torch.Generator().manual_seed(3)
+    x_last = torch.rand((1, 1, H, W), generator=g)
+    w = torch.randn((Cout, 1, 3, 3), generator=g) * 0.3
+    b = torch.randn((Cout,), generator=g)
+    x = torch.zeros((B, H, W, 1), device=cuda)
+    x[B - 1] = x_last[0].permute(1, 2, 0).to(cuda)
+    z, _ = ops.conv3x3(x, w.to(cuda), b.to(cuda))
+    want = F.conv2d(x_last.double(), w.double(), b.double(), padding=1)[0].permute(1, 2, 0)
+    got = z[B - 1].double().cpu()
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    assert torch.equal(z[0, 5, 100].cpu(), b)  # an all-zero image yields the bias

@@ -192,10 +192,11 @@ conv3x3_fwd_kernel(ConvALoad la, BLoadContigN lb, float* z, const float* bias, d
   for (int i = threadIdx.x; i < BN; i += kGemmThreads) s_sum[i] = s_sq[i] = 0.f;
   ConvFwdEpilogue<BN> ep;
   ep.z = z; ep.P = la.P; ep.N = N; ep.bias = bias; ep.stats = stats; ep.s_sum = s_sum; ep.s_sq = s_sq;
-  ep.n0 = blockIdx.x * BN;
+  // pixel tiles in grid.x (up to 2^31 - 1 of them: 512 lines x 30 x 1200 px is 144k tiles), channel tiles in grid.y
+  ep.n0 = blockIdx.y * BN;
   ep.begin();
   // gemm_tile's first __syncthreads orders the zeroing above before any shared atomic
-  gemm_tile<BN>(la, lb, ep, blockIdx.y * kGemmBM, blockIdx.x * BN, 0, 9 * la.C);
+  gemm_tile<BN>(la, lb, ep, blockIdx.x * kGemmBM, blockIdx.y * BN, 0, 9 * la.C);
 }
 
 template <int BN>
@@ -460,10 +461,10 @@ extern "C" int vocr_conv3x3_fwd_f32(const float* x, const float* wk, const float
   BLoadContigN lb;
   lb.p = wk; lb.cols = Cout; lb.ld = Cout; lb.vec = (Cout % 4 == 0) && aligned16(wk);
   if (Cout <= 64) {
-    dim3 grid(ceil_div(Cout, 64), (unsigned)ceil_div64(P, kGemmBM));
+    dim3 grid((unsigned)ceil_div64(P, kGemmBM), ceil_div(Cout, 64));
     conv3x3_fwd_kernel<64><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, Cout);
   } else {
-    dim3 grid(ceil_div(Cout, 128), (unsigned)ceil_div64(P, kGemmBM));
+    dim3 grid((unsigned)ceil_div64(P, kGemmBM), ceil_div(Cout, 128));
     conv3x3_fwd_kernel<128><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, Cout);
   }
   VOCR_CHECK_LAUNCH();

@@ -7,17 +7,17 @@ namespace vocr {
 template <int BN, class AL, class BL>
 __global__ void __launch_bounds__(kGemmThreads)
 dense_gemm_kernel(AL la, BL lb, DenseEpilogue ep, int K) {
-  gemm_tile<BN>(la, lb, ep, blockIdx.y * kGemmBM, blockIdx.x * BN, 0, K);
+  gemm_tile<BN>(la, lb, ep, blockIdx.x * kGemmBM, blockIdx.y * BN, 0, K);  // row tiles in grid.x (no 65535 limit)
 }
 
 template <class AL, class BL>
 static int launch_dense(const AL& la, const BL& lb, const DenseEpilogue& ep, int M, int N, int K,
                         cudaStream_t stream) {
   if (N <= 64) {
-    dim3 grid(ceil_div(N, 64), ceil_div(M, kGemmBM));
+    dim3 grid(ceil_div(M, kGemmBM), ceil_div(N, 64));
     dense_gemm_kernel<64, AL, BL><<<grid, kGemmThreads, 0, stream>>>(la, lb, ep, K);
   } else {
-    dim3 grid(ceil_div(N, 128), ceil_div(M, kGemmBM));
+    dim3 grid(ceil_div(M, kGemmBM), ceil_div(N, 128));
     dense_gemm_kernel<128, AL, BL><<<grid, kGemmThreads, 0, stream>>>(la, lb, ep, K);
   }
   VOCR_CHECK_LAUNCH();
