@@ -253,17 +253,26 @@ def main():
     total_kernel_ms = sum(d["ms"] for d in prof.values())
     shares = {k: d["ms"] / total_kernel_ms for k, d in prof.items()}
     NOTES = {
-        "vocr_tc_gemm_tf32x3": "TMA + tcgen05.mma kind::tf32 + TMEM, 3xTF32 (3 MMAs per product => 1/3 of the tf32 rate is "
-                               "the ceiling of this fp32-accurate mode); peak = sustained dense bf16",
+        "vocr_tc_gemm_f16x3": "TMA + tcgen05.mma kind::f16 + TMEM on FP16 pair planes, three compensated products per "
+                              "result (1/3 of the f16 rate is the ceiling of this fp32-accurate mode); peak = sustained dense bf16",
+        "vocr_tc_conv3x3_fwd_f16": "4-D TMA implicit GEMM + tcgen05 on FP16 pair planes, three products (fwd and data "
+                                   "gradient); peak = sustained dense bf16",
+        "vocr_tc_conv3x3_wgrad_f16": "4-D TMA implicit GEMM + tcgen05 on FP16 pair planes, chunked TMEM accumulation; "
+                                     "peak = sustained dense bf16",
+        "vocr_tc_gemm_tf32x3": "TMA + tcgen05.mma kind::tf32 + TMEM, 3xTF32; peak = sustained dense bf16",
         "vocr_tc_conv3x3_fwd": "4-D TMA implicit GEMM + tcgen05 3xTF32 (fwd and data gradient); peak = sustained dense bf16",
         "vocr_tc_conv3x3_wgrad": "4-D TMA implicit GEMM + tcgen05 3xTF32, chunked TMEM accumulation; peak = sustained dense bf16",
-        "vocr_bilstm_fwd_f32": "persistent recurrence, W_hh resident in smem, mma.sync 3xTF32: latency / exchange bound, "
-                               "flops = 2*T*B*8H*H; peak = sustained dense bf16",
-        "vocr_bilstm_bwd_f32": "persistent recurrence (backward), latency / exchange bound; peak = sustained dense bf16",
+        "vocr_bilstm_fwd_f32": "persistent recurrence, W_hh resident in smem as FP16 pairs, h exchanged through L2 flags: "
+                               "latency bound (T dependent steps per launch), bytes = T*2*B*5H*4 (SURVEY 8d)",
+        "vocr_bilstm_bwd_f32": "persistent recurrence (backward), partial dh reduce-scattered through L2: latency bound, "
+                               "bytes = T*2*B*10H*4",
         "vocr_gemm_f32": "fp32 FFMA engine (operands the TMA path cannot address)",
         "vocr_conv3x3_fwd_f32": "fp32 FFMA implicit GEMM (Cin < 32 layers)",
         "vocr_conv3x3_wgrad_f32": "fp32 FFMA implicit GEMM (Cin < 32 layers)",
     }
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this same cfg2 loop
+    # (profiles/r01_f16_kernels_ncu.md); kernels that run with several grids per step have no single figure
+    NCU_TRAFFIC = {"vocr_bilstm_bwd_f32": 294.9e6 + 171.4e6, "vocr_bilstm_fwd_f32": 199.4e6 + 247.1e6}
 
     def roof_of(name):
         d = prof[name]
@@ -276,7 +285,7 @@ def main():
             r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
         else:
             return None
-        r.update({"traffic": None, "step_share": shares[name], "avg_launch_ms": d["ms"] / d["calls"],
+        r.update({"traffic": NCU_TRAFFIC.get(name), "step_share": shares[name], "avg_launch_ms": d["ms"] / d["calls"],
                   "launches": d["calls"], "note": NOTES.get(name, "") + " (%s peaks)" % pk["how"]})
         return r
 

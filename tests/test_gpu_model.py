@@ -51,6 +51,18 @@ def _model(hp, n_symbols, sd, cuda):
     return m
 
 
+def _margin_small(logits, lens, n_symbols):
+    """True if some frame's decision (arg-max or the 3/|A| threshold) is within fp32 rounding of flipping - only then
+    may two correct fp32 evaluations of the same model give different transcripts."""
+    x = logits.detach().double().cpu().numpy()
+    for b in range(x.shape[1]):
+        f = x[:int(lens[b]), b]
+        top2 = np.sort(f, axis=1)[:, -2:]
+        if ((top2[:, 1] - top2[:, 0]) < 1e-4).any() or (np.abs(top2[:, 1] - 3.0 / n_symbols) < 1e-4).any():
+            return True
+    return False
+
+
 def _close(got, want, what, rtol=RTOL, atol=ATOL):
     got = torch.as_tensor(got).detach().double().cpu()
     want = torch.as_tensor(want).detach().double().cpu()
@@ -240,3 +252,44 @@ def test_full_size_cfg2_against_oracle_on_gpu(cuda):
         worst = max(worst, ours / scale)
         assert ours <= max(1e-3 * scale, 2.0 * ref32) + 1e-6, (k, ours / scale, ref32 / scale)
     assert worst <= 2e-2
+
+
+def test_decode_testset_sequence_from_raw_images(cuda):
+    """decode_testset.py:48-65,86-166 replayed from the raw decoded images: Scale(new_h=line height) -> InvertBlackWhite
+    -> ToTensor -> width-sorted padded batch -> model.eval() forward -> ArgmaxDecoder, all on the device, against the
+    chained restatements (oracle/preproc_ref.py -> model_ref.forward_ref -> decode_ref).  The batch tensor must be
+    bit-identical; logits within the fp32 bound; transcripts equal to the oracle decode of the oracle logits."""
+    from oracle.preproc_ref import preprocess_line
+    from vistaocr_b200 import ArgmaxDecoder
+    from vistaocr_b200.imagetransforms import LineBatchPreprocessor
+    hp = dict(input_line_height=30, rds_line_height=30, lstm_input_dim=32, num_lstm_layers=2,
+              num_lstm_hidden_units=40, p_lstm_dropout=0.0)
+    A = 31
+    sd = M.make_state_dict(hp, A, seed=11)
+    model = _model(hp, A, sd, cuda)
+    model.eval()
+    rng = np.random.default_rng(21)
+    raw = [rng.integers(0, 256, size=(int(h), int(w)), dtype=np.uint8)
+           for h, w in zip(rng.integers(24, 90, size=6), rng.integers(60, 420, size=6))]
+    batch, widths, order = LineBatchPreprocessor(30, invert=True, device=cuda)(raw)
+    # the reference pipeline, restated: per-image transforms, then SortByWidthCollater's padding / ordering
+    refs = [preprocess_line(im, 30, invert=True, min_width=15) for im in raw]
+    want_order = np.argsort(-np.array([r.shape[2] for r in refs]), kind="stable")
+    assert order.tolist() == want_order.tolist()
+    xw = np.zeros((len(raw), 1, 30, refs[want_order[0]].shape[2]), np.float32)
+    for b, i in enumerate(want_order):
+        xw[b, :, :, :refs[i].shape[2]] = refs[i]
+    assert np.array_equal(batch.cpu().numpy(), xw)
+    u1 = torch.from_numpy(rng.random((6, 64, 2)).astype(np.float32))
+    u2 = torch.from_numpy(rng.random((6, 128, 2)).astype(np.float32))
+    model.cnn[6]._random_samples, model.cnn[13]._random_samples = u1, u2
+    with torch.no_grad():
+        logits, lens = model(batch, widths)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    want, wlens = M.forward_ref(sd64, torch.from_numpy(xw).double(), widths.numpy(), hp, (u1, u2), training=False)
+    assert lens.tolist() == wlens.tolist()
+    _close(logits, want, "logits from raw images", rtol=2e-5)
+    hyp = ArgmaxDecoder(model.alphabet).decode(logits, lens, uxxxx=True)
+    assert hyp == decode_loop(logits.cpu().numpy(), lens.numpy(), model.alphabet.idx_to_char, uxxxx=True)
+    ref_hyp = decode_loop(want.float().numpy(), wlens.numpy(), model.alphabet.idx_to_char, uxxxx=True)
+    assert sum(a != b for a, b in zip(hyp, ref_hyp)) == 0 or _margin_small(want, wlens, A)

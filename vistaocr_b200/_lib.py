@@ -93,8 +93,11 @@ WORK = {
     "vocr_tc_conv3x3_wgrad": lambda a: ("flop", 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]),
     "vocr_conv3x3_fwd_f32": lambda a: ("flop", 2.0 * a[4] * a[5] * a[6] * 9 * a[7] * a[8]),
     "vocr_conv3x3_wgrad_f32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5] * 9 * a[6] * a[7]),
-    "vocr_bilstm_fwd_f32": lambda a: ("flop", 2.0 * a[9] * a[7] * 8 * a[8] * a[8]),
-    "vocr_bilstm_bwd_f32": lambda a: ("flop", 2.0 * a[9] * a[7] * 8 * a[8] * a[8]),
+    # the recurrent step is HBM / latency bound; per (direction, step) it reads the x-projection
+    # (B*4H) and writes h (B*H) - backward: reads dout, the gates, c and writes the gate gradients (B*10H) - W_hh and the
+    # running state stay on chip
+    "vocr_bilstm_fwd_f32": lambda a: ("byte", 4.0 * a[9] * 2 * a[7] * 5 * a[8]),
+    "vocr_bilstm_bwd_f32": lambda a: ("byte", 4.0 * a[9] * 2 * a[7] * 10 * a[8]),
     "vocr_greedy_decode_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3]),
     "vocr_ctc_loss_f32": lambda a: ("byte", 8.0 * a[5] * a[6] * a[7]),
     "vocr_clamp_adam_f32": lambda a: ("byte", 28.0 * a[4]),
