@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kDecThreads)
 argmax_path_kernel(const float* __restrict__ logits, long long n_rows, int T, int B, int A, int rows_per_tile,
                    const int32_t* __restrict__ lens, float thresh, int32_t* __restrict__ path) {
   extern __shared__ __align__(128) unsigned char dec_smem[];
+  pdl_trigger();  // the collapse kernel may be scheduled behind this grid's last wave
   const long long row0 = (long long)blockIdx.x * rows_per_tile;
   const int rows_here = (int)min((long long)rows_per_tile, n_rows - row0);
   const float* gsrc = logits + row0 * A;
@@ -121,12 +122,16 @@ collapse_compact_kernel(const int32_t* __restrict__ path, int T, int B, const in
   const int len = max(0, min(lens[b], T));
   const int32_t* p = path + (size_t)b * T;
   int32_t* out = labels + (size_t)b * ld;
+  pdl_wait();  // `path` comes from the arg-max kernel this launch depends on
   int base = 0;
   int carry = 0;  // canonical label of the frame before this chunk (0 = no previous character)
+  // the loads of chunk k + 1 are issued before chunk k is processed: the loop runs at shuffle latency, not L2 latency
+  int cur = (lane < len) ? p[lane] : 0;
+  int cc = (cur > 0) ? (canon ? canon[cur] : cur) : 0;
   for (int t0 = 0; t0 < len; t0 += 32) {
-    const int t = t0 + lane;
-    const int cur = (t < len) ? p[t] : 0;
-    const int cc = (cur > 0) ? (canon ? canon[cur] : cur) : 0;
+    const int tn = t0 + 32 + lane;
+    const int cur_n = (tn < len) ? p[tn] : 0;
+    const int cc_n = (cur_n > 0) ? (canon ? canon[cur_n] : cur_n) : 0;
     int pc = __shfl_up_sync(0xffffffffu, cc, 1);
     if (lane == 0) pc = carry;
     const bool emit = (cur > 0) && (pc != cc);
@@ -137,6 +142,8 @@ collapse_compact_kernel(const int32_t* __restrict__ path, int T, int B, const in
     }
     base += __popc(m);
     carry = __shfl_sync(0xffffffffu, cc, 31);
+    cur = cur_n;
+    cc = cc_n;
   }
   if (lane == 0) counts[b] = min(base, ld);
 }
@@ -171,8 +178,9 @@ extern "C" int vocr_greedy_decode_f32(const float* logits, int T, int B, int A, 
     }
     VOCR_CHECK_LAUNCH();
   }
-  collapse_compact_kernel<<<ceil_div(B, kDecWarps), kDecThreads, 0, stream>>>(path, T, B, lens, canon, labels,
-                                                                               counts, ld);
-  VOCR_CHECK_LAUNCH();
+  // programmatic dependent launch: the collapse grid is scheduled while the arg-max grid drains
+  if (launch_pdl(collapse_compact_kernel, dim3(ceil_div(B, kDecWarps)), dim3(kDecThreads), 0, stream, path, T, B, lens,
+                 canon, labels, counts, ld) != cudaSuccess)
+    return VOCR_EXECUTION_FAILED;
   return VOCR_OK;
 }
