@@ -49,4 +49,12 @@ def run(dev, np):
         logits, lens2 = model(torch.from_numpy(xb).to(dev), torch.from_numpy(widths))
     hyp = model.decode_without_lm(logits, lens2, uxxxx=True)
     assert hyp == decode_loop(logits.cpu().numpy(), lens2.numpy(), model.alphabet.idx_to_char, uxxxx=True)
-    print("smoke ok: decode + ctc + one training step of the full path match the oracle (loss %.4f)" % wloss)
+    # raw uint8 line images -> padded float batch (cv2-exact resize, inversion, /255) against the oracle, bit for bit
+    from oracle.preproc_ref import preprocess_line
+    from .imagetransforms import LineBatchPreprocessor
+    raw = [rng.integers(0, 256, size=(int(h), int(w)), dtype=np.uint8) for h, w in ((47, 301), (60, 400), (33, 20))]
+    pb, pw, po = LineBatchPreprocessor(30, invert=True, device=dev)(raw)
+    for k, i in enumerate(po.tolist()):
+        ref = preprocess_line(raw[i], 30, invert=True, min_width=15)
+        assert np.array_equal(pb[k, :, :, :ref.shape[2]].cpu().numpy(), ref), "pre-processing differs from the oracle"
+    print("smoke ok: pre-processing + decode + ctc + one training step of the full path match the oracle (loss %.4f)" % wloss)
