@@ -305,8 +305,19 @@ def main():
         "host_enqueue_ms_per_step": enq / args.steps,
     }
 
+    fp16_mode = None
+    if not args.no_extras:  # the same step with fp16 tensor-core operands (one product): cfg3's reduced-precision mode
+        _lib.lib().vocr_set_tc_products(1)
+        timed(resident, 2, False)
+        ms16, _, _ = timed(resident, args.steps, False)
+        _lib.lib().vocr_set_tc_products(3)
+        fp16_mode = {"lines_per_s": lines / (ms16 * 1e-3), "ms_per_step": ms16 / args.steps,
+                     "what": "same cfg2 step with set_precision('fp16'): GEMM / convolution operands fp16 (hi planes, one "
+                             "product), fp32 accumulation, activations, master weights and optimiser; NOT the headline "
+                             "value (the metric is quoted in fp32)"}
     if rank == 0 and not args.no_extras:
         out["extra"] = side_metrics(dev, model, alphabet, pk)
+        out["extra"]["train_fp16_operands"] = fp16_mode
         if world == 1:
             threads = os.cpu_count() or 1
             lps, sec = cpu_train_lines_per_s(host[0], 2, 2, 1, threads)

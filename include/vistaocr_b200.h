@@ -35,6 +35,13 @@ typedef void* vocr_stream_t; /* cudaStream_t */
 int vocr_version(void);
 const char* vocr_status_string(int status);
 
+/* Arithmetic mode of the FP16-pair tensor-core entry points (vocr_tc_gemm_f16x3, vocr_tc_conv3x3_fwd_f16,
+ * vocr_tc_conv3x3_wgrad_f16), process-wide: 3 (default) = three error-compensated products per k-step, fp32-level
+ * accuracy; 1 = one product on the hi planes only (fp16 operands, fp32 accumulation) - the reduced-precision mode of
+ * BASELINE.json's cfg3.  The reference has no counterpart (it trains in fp32, src/train_cnn_lstm.py). */
+int vocr_set_tc_products(int n);
+int vocr_get_tc_products(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Greedy CTC decode.  Replaces ArgmaxDecoder.decode (src/decoder.py:116-185) and its twin
  * CnnOcrModel.decode_without_lm (src/models/cnnlstm.py:479-541): per-frame argmax over the alphabet on RAW

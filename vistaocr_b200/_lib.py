@@ -54,6 +54,8 @@ PROTOTYPES = {
     "vocr_lm_frontend_f32": (c_int, [c_p, c_int, c_int, c_int, c_p, c_p, c_p, c_int, ctypes.c_double, c_p, c_p]),
     "vocr_edit_distance_i32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     "vocr_collate_lines_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "vocr_set_tc_products": (c_int, [c_int]),
+    "vocr_get_tc_products": (c_int, []),
     "vocr_scale_lines_u8": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
     "vocr_tc_gemm_tf32x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_int, c_p, c_int,
                                     c_p, c_int, c_int, c_p, c_sz, c_p]),

@@ -12,3 +12,18 @@ extern "C" const char* vocr_status_string(int status) {
     default: return "unknown error";
   }
 }
+
+// Arithmetic mode of the FP16-pair tensor-core kernels (vocr_tc_gemm_f16x3, vocr_tc_conv3x3_fwd_f16,
+// vocr_tc_conv3x3_wgrad_f16), process-wide like a math-mode flag:
+//   3 (default)  three error-compensated products per k-step: fp32-level accuracy (1e-5)
+//   1            one product on the hi planes: fp16 operands (11-bit mantissa, per-tensor power-of-two scaling),
+//                fp32 accumulation - the reduced-precision mode of BASELINE.json's cfg3 ("bf16 training")
+namespace vocr {
+int g_tc_products = 3;
+}
+extern "C" int vocr_set_tc_products(int n) {
+  if (n != 1 && n != 3) return VOCR_INVALID_VALUE;
+  vocr::g_tc_products = n;
+  return VOCR_OK;
+}
+extern "C" int vocr_get_tc_products(void) { return vocr::g_tc_products; }

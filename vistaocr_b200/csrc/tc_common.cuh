@@ -6,6 +6,8 @@
 
 namespace vocr {
 
+extern int g_tc_products;  // api.cu: 3 = compensated products (default), 1 = hi planes only (vocr_set_tc_products)
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

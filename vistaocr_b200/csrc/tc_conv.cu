@@ -38,6 +38,7 @@ struct TcConvParams {
   int BW, BH, tiles_x, tiles_y, BN;
   const int* exp_x;  // FP16 pair operands: device exponents of the activation / weight planes
   const int* exp_w;
+  int single;        // 1 = hi planes only, one product per k-step (vocr_set_tc_products(1))
 };
 
 template <bool F16>
@@ -89,13 +90,13 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
         const uint32_t ph = (uint32_t)(kb / kCvStages) & 1u;
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
         unsigned char* st = smem + (size_t)s * kCvStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+        mbar_arrive_expect_tx(&full_bar[s], p.single ? stage_tx / 2 : stage_tx);
         const int tap = kb / chunks, cc = kb - tap * chunks;
         const int ky = tap / 3, kx = tap - ky * 3;
         tma_load_4d(st, &map_x_hi, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
-        tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
+        if (!p.single) tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
         tma_load_2d(st + 2 * kCvTile, &map_w_hi, &full_bar[s], kb * CK, n0);
-        tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * CK, n0);
+        if (!p.single) tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * CK, n0);
       }
     }
   } else if (warp == 1) {
@@ -116,9 +117,11 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
           const uint64_t a_lo = make_desc(st + kCvTile + ks * 32, 16u, 1024u, 2u);
           const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 32, 16u, 1024u, 2u);
           const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 32, 16u, 1024u, 2u);
-          E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
-          accum_lo = 1;
-          E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+          if (!p.single) {
+            E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+            accum_lo = 1;
+            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+          }
           E::mma(tmem_base + (uint32_t)(kb % kCvHiAcc) * 128, a_hi, b_hi, idesc, (kb >= kCvHiAcc || ks > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
@@ -140,7 +143,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
       float acc[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      for (int a = 0; a <= n_hi; ++a) {
+      for (int a = 0; a < n_hi + (p.single ? 0 : 1); ++a) {
         const int which = (a == n_hi) ? kCvHiAcc : a;
         uint32_t t[32];
         tmem_ld32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(which * 128 + cb), t);
@@ -237,13 +240,13 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
           const uint32_t ph = (uint32_t)(it / kCvStages) & 1u;
           mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
           unsigned char* st = smem + (size_t)s * kCvStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          mbar_arrive_expect_tx(&full_bar[s], p.single ? stage_tx / 2 : stage_tx);
           const int tap = kb / chunks, cc = kb - tap * chunks;
           const int ky = tap / 3, kx = tap - ky * 3;
           tma_load_4d(st, &map_x_hi, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
-          tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
+          if (!p.single) tma_load_4d(st + kCvTile, &map_x_lo, &full_bar[s], cc * CK, x0 + kx - 1, y0 + ky - 1, b);
           tma_load_2d(st + 2 * kCvTile, &map_w_hi, &full_bar[s], kb * CK, n0);
-          tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * CK, n0);
+          if (!p.single) tma_load_2d(st + 3 * kCvTile, &map_w_lo, &full_bar[s], kb * CK, n0);
         }
       }
     }
@@ -270,8 +273,10 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
             const uint64_t b_hi = make_desc(st + 2 * kCvTile + ks * 32, 16u, 1024u, 2u);
             const uint64_t b_lo = make_desc(st + 3 * kCvTile + ks * 32, 16u, 1024u, 2u);
             const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-            E::mma(tmem_lo, a_lo, b_hi, idesc, acc);
-            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            if (!p.single) {
+              E::mma(tmem_lo, a_lo, b_hi, idesc, acc);
+              E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            }
             E::mma(tmem_hi, a_hi, b_hi, idesc, acc);
           }
           umma_commit(&empty_bar[s]);
@@ -312,8 +317,9 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
               float v[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const float a =
-                    fmaf(__uint_as_float(tl[q + u]), F16 ? 1.f / kPairLoScale : 1.f, __uint_as_float(th[q + u]));
+                const float a = p.single ? __uint_as_float(th[q + u])
+                                         : fmaf(__uint_as_float(tl[q + u]), F16 ? 1.f / kPairLoScale : 1.f,
+                                                __uint_as_float(th[q + u]));
                 v[u] = F16 ? scale_pow2(a, out_shift) : a;
               }
               if (p.bias) {
@@ -346,6 +352,7 @@ struct TcWgradParams {
   int xblocks;         // ceil(W / pixels per k-block)
   const int* exp_x;    // FP16 pair operands: device exponents of the x / dz planes
   const int* exp_dz;
+  int single;          // 1 = hi planes only, one product per k-step
 };
 constexpr int kWgChunk = 8;  // k-blocks per TMEM accumulation chunk
 
@@ -415,7 +422,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
           const uint32_t ph = (uint32_t)(kb / kCvStages) & 1u;
           mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
           unsigned char* st = smem + (size_t)s * kCvStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          mbar_arrive_expect_tx(&full_bar[s], p.single ? stage_tx / 2 : stage_tx);
           for (int j = 0; j < NGRP; ++j) {
             int cx, cy;
             if (tapj[j] >= 0) {
@@ -427,11 +434,12 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
               cy = p.H + 4;
             }
             tma_load_4d(st + j * E::kMnBoxBytes, &map_x_hi, &full_bar[s], cij[j], cx, cy, b);
-            tma_load_4d(st + kCvTile + j * E::kMnBoxBytes, &map_x_lo, &full_bar[s], cij[j], cx, cy, b);
+            if (!p.single) tma_load_4d(st + kCvTile + j * E::kMnBoxBytes, &map_x_lo, &full_bar[s], cij[j], cx, cy, b);
           }
           for (int j = 0; j < nb_boxes; ++j) {
             tma_load_4d(st + 2 * kCvTile + j * E::kMnBoxBytes, &map_dz_hi, &full_bar[s], n0 + MB * j, xb * PK, y, b);
-            tma_load_4d(st + 3 * kCvTile + j * E::kMnBoxBytes, &map_dz_lo, &full_bar[s], n0 + MB * j, xb * PK, y, b);
+            if (!p.single)
+              tma_load_4d(st + 3 * kCvTile + j * E::kMnBoxBytes, &map_dz_lo, &full_bar[s], n0 + MB * j, xb * PK, y, b);
           }
         }
       }
@@ -460,9 +468,11 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
             const uint64_t a_lo = make_desc(st + kCvTile + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
             const uint64_t b_hi = make_desc(st + 2 * kCvTile + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
             const uint64_t b_lo = make_desc(st + 3 * kCvTile + off, E::kMnBoxBytes, E::kMnSbo, E::kMnLayout);
-            E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
-            accum_lo = 1;
-            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            if (!p.single) {
+              E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+              accum_lo = 1;
+              E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            }
             E::mma(tmem_base + (uint32_t)a * 128, a_hi, b_hi, idesc, (kb > c * kWgChunk || ks > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
@@ -493,7 +503,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
       tc_fence_before();
       mbar_arrive(&acc_empty[a]);
     }
-    if (num_kb > 0) {
+    if (num_kb > 0 && !p.single) {
       mbar_wait_or_trap(lo_full, 0);
       tc_fence_after();
 #pragma unroll
@@ -620,6 +630,7 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
   TcConvParams p;
   p.z = z; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.exp_x = exp_x; p.exp_w = exp_w;
+  p.single = (F16 && g_tc_products == 1) ? 1 : 0;
   pick_tile(H, W, &p.BW, &p.BH);
   p.tiles_x = ceil_div(W, p.BW);
   p.tiles_y = ceil_div(H, p.BH);
@@ -697,6 +708,7 @@ static int tc_conv_wgrad_launch(const void* x_hi, const void* x_lo, const int* e
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.M = 9 * Cin; p.N = Cout;
   p.exp_x = exp_x; p.exp_dz = exp_dz;
+  p.single = (F16 && g_tc_products == 1) ? 1 : 0;
   p.BN = (Cout <= 64) ? 64 : 128;
   p.xblocks = ceil_div(W, PK);
   const int tiles = ceil_div(p.M, 128) * ceil_div(p.N, p.BN);

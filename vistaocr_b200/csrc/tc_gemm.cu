@@ -38,6 +38,8 @@ struct TcGemmParams {
   int kb_per_split;
   const int* exp_a;  // FP16 pair operands: planes hold A * 2^exp_a[0], B * 2^exp_b[0] (device scalars)
   const int* exp_b;
+  int single;        // 1 = one product per k-step on the hi planes only (reduced-precision mode: fp16 operands, fp32
+                     //     accumulation; the lo planes are neither loaded nor multiplied)
 };
 constexpr int kTcChunk = 8;  // k-blocks accumulated in TMEM before the epilogue warps drain them into fp32 registers
 
@@ -94,24 +96,26 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
         unsigned char* st = smem + (size_t)s * kTcStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
+        mbar_arrive_expect_tx(&full_bar[s], p.single ? kTcStageBytes / 2 : kTcStageBytes);
         const int k0 = kb * BK;
         if (!p.a_mn) {
           tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
-          tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
+          if (!p.single) tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
         } else {
           for (int j = 0; j < kTcBM / E::kMnBox; ++j) {                        // boxes {32|64 m, BK k rows}
             tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
-            tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
+            if (!p.single)
+              tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
           }
         }
         if (!p.b_mn) {
           tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
-          tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          if (!p.single) tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
         } else {
           for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
             tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
-            tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
+            if (!p.single)
+              tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
           }
         }
       }
@@ -145,9 +149,11 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
           const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
           const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
-          E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
-          accum_lo = 1;
-          E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+          if (!p.single) {
+            E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+            accum_lo = 1;
+            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+          }
           E::mma(tmem_base + (uint32_t)(kb % kTcHiAcc) * kTcBN, a_hi, b_hi, idesc,
                  (kb >= kTcHiAcc || ks > 0) ? 1u : 0u);
         }
@@ -169,7 +175,7 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       float r[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] = 0.f;
-      for (int acc = 0; acc <= n_hi; ++acc) {  // acc == n_hi -> the lo accumulator
+      for (int acc = 0; acc < n_hi + (p.single ? 0 : 1); ++acc) {  // acc == n_hi -> the lo accumulator
         const int which = (acc == n_hi) ? kTcHiAcc : acc;
         uint32_t t[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(which * kTcBN + cb);
@@ -284,24 +290,26 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
           const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
           mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
           unsigned char* st = smem + (size_t)s * kTcStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
+          mbar_arrive_expect_tx(&full_bar[s], p.single ? kTcStageBytes / 2 : kTcStageBytes);
           const int k0 = kb * BK;
           if (!p.a_mn) {
             tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
-            tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
+            if (!p.single) tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
           } else {
             for (int j = 0; j < kTcBM / E::kMnBox; ++j) {
               tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
-              tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
+              if (!p.single)
+                tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
             }
           }
           if (!p.b_mn) {
             tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
-            tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+            if (!p.single) tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
           } else {
             for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
               tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
-              tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
+              if (!p.single)
+                tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
             }
           }
         }
@@ -335,8 +343,10 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
             const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
             const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
-            E::mma(tmem_lo, a_lo, b_hi, idesc, acc);
-            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            if (!p.single) {
+              E::mma(tmem_lo, a_lo, b_hi, idesc, acc);
+              E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            }
             E::mma(tmem_hi, a_hi, b_hi, idesc, acc);
           }
           umma_commit(&empty_bar[s]);
@@ -367,7 +377,8 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
         float r[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          const float v = fmaf(__uint_as_float(tl[q]), F16 ? 1.f / kPairLoScale : 1.f, __uint_as_float(th[q]));
+          const float v = p.single ? __uint_as_float(th[q])
+                                   : fmaf(__uint_as_float(tl[q]), F16 ? 1.f / kPairLoScale : 1.f, __uint_as_float(th[q]));
           r[q] = F16 ? scale_pow2(v, out_shift) : v;
         }
         if (m < p.M) {
@@ -467,24 +478,26 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const uint32_t ph = (uint32_t)(i / kTcStages) & 1u;
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
         unsigned char* st = smem + (size_t)s * kTcStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], kTcStageBytes);
+        mbar_arrive_expect_tx(&full_bar[s], p.single ? kTcStageBytes / 2 : kTcStageBytes);
         const int k0 = (kb_begin + i) * BK;
         if (!p.a_mn) {
           tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
-          tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
+          if (!p.single) tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
         } else {
           for (int j = 0; j < kTcBM / E::kMnBox; ++j) {                        // boxes {32|64 m, BK k rows}
             tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
-            tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
+            if (!p.single)
+              tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
           }
         }
         if (!p.b_mn) {
           tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
-          tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          if (!p.single) tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
         } else {
           for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
             tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
-            tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
+            if (!p.single)
+              tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
           }
         }
       }
@@ -519,9 +532,11 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const uint64_t a_lo = make_desc(st + kTcTileBytes + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t b_hi = make_desc(st + 2 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
             const uint64_t b_lo = make_desc(st + 3 * kTcTileBytes + ks * b_step, b_lbo, b_sbo, b_lt);
-            E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
-            accum_lo = 1;
-            E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            if (!p.single) {
+              E::mma(tmem_lo, a_lo, b_hi, idesc, accum_lo);
+              accum_lo = 1;
+              E::mma(tmem_lo, a_hi, b_lo, idesc, 1);
+            }
             E::mma(tmem_base + (uint32_t)a * kTcBN, a_hi, b_hi, idesc, (i > c * chunk_len || ks > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
@@ -551,7 +566,7 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       tc_fence_before();
       mbar_arrive_cta(&acc_empty[a]);
     }
-    if (num_kb > 0) {
+    if (num_kb > 0 && !p.single) {
       mbar_wait_or_trap(lo_full, 0);
       tc_fence_after();
 #pragma unroll
@@ -860,7 +875,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   int kb_per_split = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kb_per_split);
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
-                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b};
+                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, (F16 && g_tc_products == 1) ? 1 : 0};
   dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
   if (splits == 1 && total_kb <= kTcPersistMaxKb)
     tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(

@@ -109,6 +109,24 @@ USE_TC = _os.environ.get("VOCR_TC", "1") != "0"
 USE_F16 = USE_TC and _os.environ.get("VOCR_F16", "1") != "0"
 
 
+def set_precision(mode):
+    """Arithmetic of the tensor-core GEMM / convolution kernels, process-wide (vocr_set_tc_products):
+    "fp32" (default) - three error-compensated products on FP16 pair planes, results within 1e-5 of fp32 (cfg2);
+    "fp16"           - one product on the hi planes: fp16 operands (11-bit mantissa, per-tensor power-of-two scaling),
+                       fp32 accumulation, fp32 activations / master weights / optimiser - the reduced-precision
+                       training mode of BASELINE.json's cfg3.  The BiLSTM recurrence keeps its compensated products.
+    Returns the previous mode."""
+    prev = "fp16" if lib().vocr_get_tc_products() == 1 else "fp32"
+    if mode not in ("fp32", "fp16"):
+        raise ValueError("precision must be 'fp32' or 'fp16'")
+    check(lib().vocr_set_tc_products(1 if mode == "fp16" else 3), "vocr_set_tc_products")
+    return prev
+
+
+def get_precision():
+    return "fp16" if lib().vocr_get_tc_products() == 1 else "fp32"
+
+
 class Operand:
     """A GEMM operand: the fp32 tensor plus, lazily, its (hi, lo) TF32 split (shared by every GEMM that reads it)."""
 
