@@ -18,48 +18,46 @@ __device__ __forceinline__ int fmp_start(float u, int i, int in_size, int out_si
   return (int)a - (int)b;
 }
 
+// grid = (chunks of Wo*C, Ho, B): the only division left per element is the 32-bit q / C
 __global__ void __launch_bounds__(256)
 fracpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ samples, float* __restrict__ y,
                     int32_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
-  const long long total = (long long)B * Ho * Wo * C;
-  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-       o += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(o % C);
-    const int wo = (int)((o / C) % Wo);
-    const int ho = (int)((o / ((long long)C * Wo)) % Ho);
-    const int b = (int)(o / ((long long)C * Wo * Ho));
-    const float uw = __ldg(samples + ((size_t)b * C + c) * 2 + 0);
-    const float uh = __ldg(samples + ((size_t)b * C + c) * 2 + 1);
-    const int w0 = fmp_start(uw, wo, W, Wo);
-    const int h0 = fmp_start(uh, ho, H, Ho);
-    const float* xb = x + (size_t)b * H * W * C + c;
+  const int ho = blockIdx.y, b = blockIdx.z;
+  const unsigned row_elems = (unsigned)Wo * (unsigned)C;
+  const float* xb = x + (size_t)b * H * W * C;
+  const size_t orow = ((size_t)b * Ho + ho) * row_elems;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < row_elems; q += gridDim.x * blockDim.x) {
+    const unsigned wo = q / (unsigned)C;
+    const int c = (int)(q - wo * (unsigned)C);
+    const float* up = samples + ((size_t)b * C + c) * 2;  // (u_w, u_h)
+    const int w0 = fmp_start(__ldg(up), (int)wo, W, Wo);
+    const int h0 = fmp_start(__ldg(up + 1), ho, H, Ho);
+    const int p00 = h0 * W + w0;
+    const float* xp = xb + (size_t)p00 * C + c;
+    const float v00 = __ldg(xp), v01 = __ldg(xp + C), v10 = __ldg(xp + (size_t)W * C), v11 = __ldg(xp + (size_t)(W + 1) * C);
     float best = -INFINITY;
-    int bi = h0 * W + w0;
-#pragma unroll
-    for (int dh = 0; dh < 2; ++dh)
-#pragma unroll
-      for (int dw = 0; dw < 2; ++dw) {
-        const int p = (h0 + dh) * W + (w0 + dw);
-        const float v = __ldg(xb + (size_t)p * C);
-        if (v > best || v != v) {
-          best = v;
-          bi = p;
-        }
-      }
-    y[o] = best;
-    if (idx) idx[o] = bi;
+    int bi = p00;
+    // (h, w) scan order with ATen's `val > max || isnan(val)` rule
+    if (v00 > best || v00 != v00) best = v00, bi = p00;
+    if (v01 > best || v01 != v01) best = v01, bi = p00 + 1;
+    if (v10 > best || v10 != v10) best = v10, bi = p00 + W;
+    if (v11 > best || v11 != v11) best = v11, bi = p00 + W + 1;
+    y[orow + q] = best;
+    if (idx) idx[orow + q] = bi;
   }
 }
 
 __global__ void __launch_bounds__(256)
 fracpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx, float* __restrict__ dx, int B,
                     int HW, int C, int HoWo) {
-  const long long total = (long long)B * HoWo * C;
-  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-       o += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(o % C);
-    const int b = (int)(o / ((long long)C * HoWo));
-    atomicAdd(dx + ((size_t)b * HW + idx[o]) * C + c, dy[o]);
+  // grid = (chunks of HoWo*C, B): 32-bit index arithmetic inside a sample
+  const int b = blockIdx.y;
+  const unsigned per = (unsigned)HoWo * (unsigned)C;
+  const size_t o0 = (size_t)b * per;
+  float* dxb = dx + (size_t)b * HW * C;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
+    const unsigned c = q % (unsigned)C;
+    atomicAdd(dxb + (size_t)__ldg(idx + o0 + q) * C + c, __ldg(dy + o0 + q));
   }
 }
 
@@ -74,7 +72,8 @@ extern "C" int vocr_fracpool_fwd_f32(const float* x, const float* samples, float
   const long long total = (long long)B * Ho * Wo * C;
   if (total == 0) return VOCR_OK;
   VOCR_REQUIRE(x && samples && y);
-  const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
+  VOCR_REQUIRE((long long)Wo * C < (1ll << 31) && Ho <= 65535 && B <= 65535);
+  dim3 grid((unsigned)min(64ll, ceil_div64((long long)Wo * C, 256)), (unsigned)Ho, (unsigned)B);
   fracpool_fwd_kernel<<<grid, 256, 0, stream>>>(x, samples, y, idx, B, H, W, C, Ho, Wo);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
@@ -89,7 +88,8 @@ extern "C" int vocr_fracpool_bwd_f32(const float* dy, const int32_t* idx, float*
   const long long total = (long long)B * Ho * Wo * C;
   if (total == 0) return VOCR_OK;
   VOCR_REQUIRE(dy && idx);
-  const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
+  VOCR_REQUIRE((long long)Ho * Wo * C < (1ll << 31) && B <= 65535);
+  dim3 grid((unsigned)min((long long)kNumSMs * 4, ceil_div64((long long)Ho * Wo * C, 256)), (unsigned)B);
   fracpool_bwd_kernel<<<grid, 256, 0, stream>>>(dy, idx, dx, B, H * W, C, Ho * Wo);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
