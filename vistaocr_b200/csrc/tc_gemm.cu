@@ -717,6 +717,7 @@ split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* _
 // FP16 pair planes cols[p][tap*C + c] = x[p + tap][c] * 2^e (zero outside the image).  With so few channels the
 // implicit-GEMM conv kernels would move 128-byte swizzle rows that are mostly padding; a K = 9C GEMM over these planes
 // (forward: cols W^T, weight gradient: cols^T dz) runs on the kind::f16 GEMM kernels instead.
+template <typename IDX>  // unsigned when the plane has < 2^31 4-element groups (64-bit divisions made it instruction-bound)
 __global__ void __launch_bounds__(256)
 im2col3x3_f16_kernel(const float* __restrict__ x, int B, int H, int W, int C4, __half* __restrict__ hi,
                      __half* __restrict__ lo, const unsigned* __restrict__ bound_bits, int* __restrict__ exp_out) {
@@ -724,15 +725,15 @@ im2col3x3_f16_kernel(const float* __restrict__ x, int B, int H, int W, int C4, _
   if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
   const float sc = exp2i(e);
   const long long total = (long long)B * H * W * 9 * C4;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(idx % C4);
-    long long r = idx / C4;
-    const int tap = (int)(r % 9);
-    r /= 9;  // pixel
-    const int xx = (int)(r % W);
-    const int yy = (int)((r / W) % H);
-    const long long b = r / ((long long)W * H);
+  for (IDX idx = (IDX)blockIdx.x * blockDim.x + threadIdx.x; idx < (IDX)total; idx += (IDX)gridDim.x * blockDim.x) {
+    const IDX r9 = idx / (IDX)C4;
+    const int c4 = (int)(idx - r9 * (IDX)C4);
+    const IDX r = r9 / 9;  // pixel
+    const int tap = (int)(r9 - r * 9);
+    const IDX row = r / (IDX)W;
+    const int xx = (int)(r - row * (IDX)W);
+    const long long b = (long long)(row / (IDX)H);
+    const int yy = (int)(row - (IDX)b * (IDX)H);
     const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sy >= 0 && sy < H && sx >= 0 && sx < W)
@@ -811,8 +812,12 @@ extern "C" int vocr_im2col3x3_f16(const float* x, int B, int H, int W, int C, co
                ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0);
   const long long total = n * 9 / 4;
   const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
-  im2col3x3_f16_kernel<<<grid, 256, 0, stream>>>(x, B, H, W, C / 4, reinterpret_cast<__half*>(hi),
-                                                 reinterpret_cast<__half*>(lo), bits, state);
+  if (total + (long long)grid * 256 < (1ll << 31))
+    im2col3x3_f16_kernel<unsigned><<<grid, 256, 0, stream>>>(x, B, H, W, C / 4, reinterpret_cast<__half*>(hi),
+                                                             reinterpret_cast<__half*>(lo), bits, state);
+  else
+    im2col3x3_f16_kernel<long long><<<grid, 256, 0, stream>>>(x, B, H, W, C / 4, reinterpret_cast<__half*>(hi),
+                                                              reinterpret_cast<__half*>(lo), bits, state);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }
