@@ -660,7 +660,8 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
   const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
   const int n_tiles = ceil_div(Cout, p.BN);
   VOCR_REQUIRE(tiles * n_tiles <= 2147483647LL);
-  if (9 * (Cin / CK) <= kCvPersistMaxKb) {
+  // (the K limit of the persistent kernel protects the fp32-level accuracy; the single-product mode has no such claim)
+  if (9 * (Cin / CK) <= kCvPersistMaxKb || p.single) {
     const int total = (int)(tiles * n_tiles);
     tc_conv_fwd_persist_kernel<F16><<<min(total, kNumSMs), kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, mw_hi,
                                                                                                 mw_lo, p, n_tiles, total);

@@ -882,7 +882,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
                  b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, (F16 && g_tc_products == 1) ? 1 : 0};
   dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
-  if (splits == 1 && total_kb <= kTcPersistMaxKb)
+  if (splits == 1 && (total_kb <= kTcPersistMaxKb || p.single))
     tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, p, ceil_div(N, kTcBN), tiles);
   else if (splits == 1 && total_kb <= 96)
