@@ -38,3 +38,26 @@ def test_product_never_imports_the_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py") and fn != "_smoke.py":
             assert "oracle" not in open(os.path.join(pkg, fn)).read(), fn
+
+
+def test_precision_switch_is_host_only_state():
+    import pytest
+    import vistaocr_b200
+    assert vistaocr_b200.get_precision() == "fp32"
+    assert vistaocr_b200.set_precision("fp16") == "fp32" and vistaocr_b200.get_precision() == "fp16"
+    assert vistaocr_b200.set_precision("fp32") == "fp16" and vistaocr_b200.get_precision() == "fp32"
+    with pytest.raises(ValueError):
+        vistaocr_b200.set_precision("bf16")
+    from vistaocr_b200 import _lib
+    assert _lib.lib().vocr_set_tc_products(2) != 0 and _lib.lib().vocr_get_tc_products() == 3
+
+
+def test_scaled_width_matches_the_reference_formula():
+    """imagetransforms.py:470-478: int(w * float(new_h / h)) in Python floats; the product's host helper and the
+    oracle's must agree everywhere (the kernel takes the width from the host)."""
+    from oracle.preproc_ref import scaled_width as ref
+    from vistaocr_b200.imagetransforms import scaled_width
+    for h in (7, 24, 30, 47, 60, 61, 120, 333):
+        for w in (1, 2, 9, 15, 100, 301, 733, 1999, 2000):
+            for new_h in (30, 60, 120):
+                assert scaled_width(h, w, new_h) == ref(h, w, new_h) == max(1, int(w * float(new_h / h)))
