@@ -307,10 +307,11 @@ def main():
 
     fp16_mode = None
     if not args.no_extras:  # the same step with fp16 tensor-core operands (one product): cfg3's reduced-precision mode
-        _lib.lib().vocr_set_tc_products(1)
+        import vistaocr_b200
+        vistaocr_b200.set_precision("fp16")
         timed(resident, 2, False)
         ms16, _, _ = timed(resident, args.steps, False)
-        _lib.lib().vocr_set_tc_products(3)
+        vistaocr_b200.set_precision("fp32")
         fp16_mode = {"lines_per_s": lines / (ms16 * 1e-3), "ms_per_step": ms16 / args.steps,
                      "what": "same cfg2 step with set_precision('fp16'): GEMM / convolution operands fp16 (hi planes, one "
                              "product), fp32 accumulation, activations, master weights and optimiser; NOT the headline "

@@ -36,9 +36,11 @@ int vocr_version(void);
 const char* vocr_status_string(int status);
 
 /* Arithmetic mode of the FP16-pair tensor-core entry points (vocr_tc_gemm_f16x3, vocr_tc_conv3x3_fwd_f16,
- * vocr_tc_conv3x3_wgrad_f16), process-wide: 3 (default) = three error-compensated products per k-step, fp32-level
- * accuracy; 1 = one product on the hi planes only (fp16 operands, fp32 accumulation) - the reduced-precision mode of
- * BASELINE.json's cfg3.  The reference has no counterpart (it trains in fp32, src/train_cnn_lstm.py). */
+ * vocr_tc_conv3x3_wgrad_f16): 3 = three error-compensated products per k-step, fp32-level accuracy; 1 = one product on
+ * the hi planes only (fp16 operands, fp32 accumulation) - the reduced-precision mode of BASELINE.json's cfg3.  Those
+ * entry points take the mode PER CALL (`products`); the setter below only changes what `products = 0` means (an atomic
+ * process default, 3 initially) - no launch path reads shared mutable state otherwise.  The reference has no counterpart
+ * (it trains in fp32, src/train_cnn_lstm.py). */
 int vocr_set_tc_products(int n);
 int vocr_get_tc_products(void);
 
@@ -148,7 +150,8 @@ int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float* scale, co
 
 /* FractionalMaxPool2d(2, output_ratio=(0.5,0.7)) with explicit per-(sample,channel) samples[B,C,2]
  * (src/models/cnnlstm.py:127,130; ATen interval rule, random in train AND eval).  idx (int32, may be NULL) keeps the
- * flat input position h*W+w of each winner; backward scatter-adds dy through idx into dx (zeroed inside). */
+ * flat input position h*W+w of each winner; backward scatters dy through idx into dx (zeroed inside) in four
+ * race-free passes over the (row parity, column parity) classes of the windows: deterministic, no atomics. */
 int vocr_fracpool_fwd_f32(const float* x, const float* samples, float* y, int32_t* idx, int B, int H, int W, int C,
                           int Ho, int Wo, vocr_stream_t stream);
 int vocr_fracpool_bwd_f32(const float* dy, const int32_t* idx, float* dx, int B, int H, int W, int C, int Ho,
@@ -171,6 +174,20 @@ int vocr_bilstm_fwd_f32(const float* xproj, const float* whh, const int32_t* len
 int vocr_bilstm_bwd_f32(const float* dout, const float* whh, const int32_t* lens, const float* gates,
                         const float* cst, float* dgates, int T, int B, int H, int Tmax, void* workspace,
                         size_t workspace_bytes, vocr_stream_t stream);
+
+/* Inter-layer LSTM dropout (nn.LSTM(dropout=p), src/models/cnnlstm.py:148-149; p = 0.5 at src/train_cnn_lstm.py:331;
+ * training only, on the output of every layer but the last).  y[i] = keep[i] ? x[i] * 1/(1-p) : 0 (in place allowed).
+ * keep comes from mask_in (uint8[n], 1 = keep) when given - the parity tests inject the oracle's mask - else from a
+ * Philox4x32-10 counter stream: element i uses word i&3 of Philox(counter {i>>2, offset}, key seed), kept iff
+ * word >= floor(p 2^32).  Nothing is stored: the backward pass is the same call on dy with the same (seed, offset).
+ * rng (device uint64[2] = {seed, offset}, optional) replaces `seed` and is ADDED to `offset`, so a captured CUDA graph
+ * draws a fresh mask per replay (vocr_rng_advance bumps rng[1] on the stream); rng_used (device uint64[2], optional)
+ * receives the effective pair for the backward call.  mask_out (optional) receives the keep mask; x = y = NULL with
+ * mask_out set only writes the mask. */
+int vocr_dropout_f32(const float* x, float* y, long long n, float p, const unsigned long long* rng,
+                     unsigned long long seed, unsigned long long offset, unsigned long long* rng_used,
+                     const uint8_t* mask_in, uint8_t* mask_out, vocr_stream_t stream);
+int vocr_rng_advance(unsigned long long* rng, unsigned long long inc, vocr_stream_t stream);
 
 /* Fused element-wise gradient clamp to [-clamp,clamp] + torch.optim.Adam update over a flat parameter buffer
  * (src/train_cnn_lstm.py:143-149,363).  step >= 1; clamp <= 0 disables; grad_scale pre-multiplies the gradient. */
@@ -200,6 +217,8 @@ int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_
  *   (when NULL an absmax pass computes it).  Everything stays on the stream - no host synchronisation.
  * vocr_tc_gemm_f16x3 / vocr_tc_conv3x3_fwd_f16 / vocr_tc_conv3x3_wgrad_f16: as their TF32 namesakes, taking the planes
  *   and the device exponent of each operand; lda / ldb multiples of 8, Cin % 64 == 0 (and Cout % 64 == 0 for wgrad).
+ *   products: arithmetic mode of THIS call - 3 = three compensated products (fp32-level), 1 = hi planes only (fp16
+ *   operands, fp32 accumulation), 0 = the process default of vocr_set_tc_products.
  * ---------------------------------------------------------------------------------------------------------- */
 int vocr_split_f16_f32(const float* x, long long n, const float* bound, int32_t* state, uint16_t* hi, uint16_t* lo,
                        vocr_stream_t stream);
@@ -211,13 +230,13 @@ int vocr_im2col3x3_f16(const float* x, int B, int H, int W, int C, const float* 
 int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const uint16_t* a_hi, const uint16_t* a_lo, int lda,
                        const int32_t* exp_a, const uint16_t* b_hi, const uint16_t* b_lo, int ldb, const int32_t* exp_b,
                        float* C, int ldc, const float* bias, int relu, int accumulate, void* workspace,
-                       size_t workspace_bytes, vocr_stream_t stream);
+                       size_t workspace_bytes, int products, vocr_stream_t stream);
 int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* w_hi,
                             const uint16_t* w_lo, const int32_t* exp_w, const float* bias, float* z, int B, int H, int W,
-                            int Cin, int Cout, vocr_stream_t stream);
+                            int Cin, int Cout, int products, vocr_stream_t stream);
 int vocr_tc_conv3x3_wgrad_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* dz_hi,
                               const uint16_t* dz_lo, const int32_t* exp_dz, float* dw, int B, int H, int W, int Cin,
-                              int Cout, void* workspace, size_t workspace_bytes, vocr_stream_t stream);
+                              int Cout, void* workspace, size_t workspace_bytes, int products, vocr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3x3 convolutions on the tensor cores (4-D TMA implicit GEMM + tcgen05 3xTF32), same math as vocr_conv3x3_fwd_f32 /

@@ -38,7 +38,17 @@ CONFIGS = {
                  num_lstm_hidden_units=16, p_lstm_dropout=0.0), 29, 3, 60, 150, 12),
     "h120": (dict(input_line_height=120, rds_line_height=30, lstm_input_dim=8, num_lstm_layers=1,
                   num_lstm_hidden_units=8, p_lstm_dropout=0.0), 7, 2, 90, 200, 13),
+    # the benchmarked architecture itself (BASELINE cfg2: D128 / 3x512 BiLSTM, h 60 -> rds 30, alphabet 96), small
+    # batch: pins H = 512 / K = 1024 / K = 2304 arithmetic to the REAL reference, not to the port
+    "cfg2arch": (dict(input_line_height=60, rds_line_height=30, lstm_input_dim=128, num_lstm_layers=3,
+                      num_lstm_hidden_units=512, p_lstm_dropout=0.0), 96, 3, 120, 260, 14),
 }
+# strided slices of the large gradient tensors (a full cnn.21.weight gradient alone would be 2.4 MB)
+GRAD_SLICES = {"lstm.weight_hh_l1": (slice(None, None, 64), slice(None, None, 16)),
+               "lstm.weight_ih_l2_reverse": (slice(None, None, 64), slice(None, None, 32)),
+               "cnn.17.weight": (slice(None, None, 8), slice(None, None, 8)),
+               "bridge_layer.0.weight": (slice(None, None, 4), slice(None, None, 16)),
+               "prob_layer.0.weight": (slice(None, None, 3), slice(None, None, 16))}
 GRAD_KEYS = ["prob_layer.0.bias", "bridge_layer.0.bias", "cnn.0.weight", "cnn.1.weight", "cnn.1.bias",
              "cnn.21.weight", "lstm.bias_hh_l0", "lstm.bias_ih_l0_reverse"]
 
@@ -80,9 +90,16 @@ def model_fixture(name):
     out["train_logits"] = logits.detach().numpy()
     out["train_loss"] = np.float64(loss.item())
     named = dict(model.named_parameters())
+    big = name == "cfg2arch"
     for k in GRAD_KEYS:
-        if k in named:
+        if k in named and not (big and named[k].numel() > 20000):
             out["grad." + k] = named[k].grad.numpy()
+    if big:
+        for k, sl in GRAD_SLICES.items():
+            out["gradslice." + k] = named[k].grad[sl].contiguous().numpy()
+            out["gradmax." + k] = np.float64(named[k].grad.abs().max().item())
+        out["grad.rapid_ds.00-conv.weight"] = named["rapid_ds.00-conv.weight"].grad.numpy()
+        out["grad.lstm.bias_hh_l2"] = named["lstm.bias_hh_l2"].grad.numpy()
     msd = model.state_dict()
     for k in ("cnn.1.running_mean", "cnn.1.running_var", "cnn.21.running_mean", "cnn.21.running_var"):
         out["after." + k] = msd[k].numpy()
@@ -114,6 +131,9 @@ def decode_fixture():
 
 
 if __name__ == "__main__":
-    decode_fixture()
+    only = sys.argv[1:]
+    if not only:
+        decode_fixture()
     for name in CONFIGS:
-        model_fixture(name)
+        if not only or name in only:
+            model_fixture(name)

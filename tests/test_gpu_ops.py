@@ -157,6 +157,11 @@ def test_fracpool_bit_exact(cuda, B, H, W, C):
     yo.backward(nhwc(dy).to(cuda))
     assert torch.equal(nchw(yo).cpu(), yr.detach())
     close(nchw(xo.grad), xr.grad, rtol=1e-6, what="fracpool dx")
+    # the backward scatter is deterministic (four race-free parity passes, no atomics): bit-identical reruns
+    g1 = xo.grad.clone()
+    xo.grad = None
+    ops.fracpool(xo, u.to(cuda)).backward(nhwc(dy).to(cuda))
+    assert torch.equal(g1, xo.grad)
     # and the oracle's own restatement of the interval rule
     assert torch.equal(M.fmp_ref(x[:1, :4], u[:1, :4]), yr.detach()[:1, :4])
 
@@ -213,6 +218,61 @@ def test_clamp_adam_matches_torch(cuda):
         opt.step()
         ops.clamp_adam_step(po, grad.to(cuda), m, v, step, lr=1e-3, weight_decay=0.01, clamp=5.0)
         close(po, pr, rtol=2e-6, what="adam step %d" % step)
+
+
+def test_clamp_adam_state_dict_round_trip_and_adam_compat(cuda):
+    """The reference snapshots `optimizer.state_dict()` (train_cnn_lstm.py:427-438): a resumed run must continue with
+    the same moments and step count, and the format is torch.optim.Adam's (both directions)."""
+    from vistaocr_b200 import ClampAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(7, 3), (5,), (2, 3, 3)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) * 3 for s in shapes] for _ in range(5)]
+
+    def params():
+        return [torch.nn.Parameter(t.clone().to(cuda)) for t in init]
+
+    def run(opt, ps, steps):
+        for gs in steps:
+            opt.zero_grad()
+            for p, gr in zip(ps, gs):
+                if p.grad is None:
+                    p.grad = gr.clone().to(cuda)
+                else:
+                    p.grad.copy_(gr.to(cuda))
+            if not isinstance(opt, ClampAdam):
+                for p in ps:
+                    p.grad.clamp_(-5, 5)
+            opt.step()
+
+    pa = params()
+    a = ClampAdam(pa, lr=1e-2)
+    assert a.state_dict()["state"] == {}  # nothing to save before the first step
+    run(a, pa, grads[:3])
+    sd = a.state_dict()
+    assert sorted(sd["state"]) == [0, 1, 2] and float(sd["state"][0]["step"]) == 3.0
+    assert sd["state"][2]["exp_avg"].shape == (2, 3, 3) and sd["param_groups"][0]["lr"] == 1e-2
+    # resume into a fresh ClampAdam: identical continuation
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    b = ClampAdam(pb, lr=1e-2)
+    b.load_state_dict(sd)
+    run(a, pa, grads[3:])
+    run(b, pb, grads[3:])
+    for x, y in zip(pa, pb):
+        assert torch.equal(x, y)
+    # the same snapshot resumes torch.optim.Adam, and Adam's snapshot resumes ClampAdam
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pb]
+    c = torch.optim.Adam(pc, lr=1e-2)
+    c.load_state_dict(b.state_dict())
+    pd = [torch.nn.Parameter(p.detach().clone()) for p in pb]
+    d = ClampAdam(pd, lr=1e-2)
+    d.load_state_dict(c.state_dict())
+    run(c, pc, grads[:2])
+    run(d, pd, grads[:2])
+    run(b, pb, grads[:2])
+    for x, y, z in zip(pb, pc, pd):
+        assert torch.equal(x, z)
+        close(y, x, rtol=2e-6, what="torch Adam resumed from a ClampAdam snapshot")
 
 
 @pytest.mark.parametrize("rows,cols,ld", [(1000, 64, 64), (18560, 4096, 4096), (37, 96, 100), (513, 97, 97), (5, 8, 8)])

@@ -17,7 +17,15 @@ CONFIGS = {
                 num_lstm_hidden_units=16, p_lstm_dropout=0.0),
     "h120": dict(input_line_height=120, rds_line_height=30, lstm_input_dim=8, num_lstm_layers=1,
                  num_lstm_hidden_units=8, p_lstm_dropout=0.0),
+    # the benchmarked architecture (BASELINE cfg2: D128 / 3x512), fixture generated from the REAL reference
+    "cfg2arch": dict(input_line_height=60, rds_line_height=30, lstm_input_dim=128, num_lstm_layers=3,
+                     num_lstm_hidden_units=512, p_lstm_dropout=0.0),
 }
+GRAD_SLICES = {"lstm.weight_hh_l1": (slice(None, None, 64), slice(None, None, 16)),
+               "lstm.weight_ih_l2_reverse": (slice(None, None, 64), slice(None, None, 32)),
+               "cnn.17.weight": (slice(None, None, 8), slice(None, None, 8)),
+               "bridge_layer.0.weight": (slice(None, None, 4), slice(None, None, 16)),
+               "prob_layer.0.weight": (slice(None, None, 3), slice(None, None, 16))}
 
 
 @pytest.mark.parametrize("A", [5, 97, 120, 121])
@@ -31,7 +39,7 @@ def test_decode_oracle_matches_reference_fixture(A):
     assert [" ".join(idx_to_char[k] for k in l) for l in labs] == z["A%d.hyp" % A].tolist()
 
 
-@pytest.mark.parametrize("name", ["h30", "h60", "h120"])
+@pytest.mark.parametrize("name", ["h30", "h60", "h120", "cfg2arch"])
 def test_model_oracle_matches_reference_fixture(name):
     hp = CONFIGS[name]
     z = np.load(os.path.join(GOLD, "model_%s.npz" % name))
@@ -57,6 +65,9 @@ def test_model_oracle_matches_reference_fixture(name):
     for k in z.files:
         if k.startswith("grad."):
             assert np.abs(params[k[5:]].grad.numpy() - z[k]).max() <= 1e-4 * np.abs(z[k]).max() + 1e-6, k
+        if k.startswith("gradslice."):
+            got = params[k[10:]].grad[GRAD_SLICES[k[10:]]].numpy()
+            assert np.abs(got - z[k]).max() <= 1e-4 * float(z["gradmax." + k[10:]]) + 1e-6, k
         if k.startswith("after."):
             assert np.abs(upd[k[6:]].numpy() - z[k]).max() <= 1e-6, k
 

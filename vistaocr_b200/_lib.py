@@ -16,6 +16,7 @@ c_f = ctypes.c_float
 c_sz = ctypes.c_size_t
 c_p = ctypes.c_void_p
 c_ll = ctypes.c_longlong
+c_ull = ctypes.c_ulonglong
 
 # name -> (restype, argtypes); must list every symbol declared in include/vistaocr_b200.h
 PROTOTYPES = {
@@ -46,6 +47,8 @@ PROTOTYPES = {
     "vocr_bilstm_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_bilstm_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_clamp_adam_f32": (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
+    "vocr_dropout_f32": (c_int, [c_p, c_p, c_ll, c_f, c_p, c_ull, c_ull, c_p, c_p, c_p, c_p]),
+    "vocr_rng_advance": (c_int, [c_p, c_ull, c_p]),
     "vocr_split_tf32_f32": (c_int, [c_p, c_p, c_p, c_ll, c_p]),
     "vocr_tc_conv3x3_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p]),
     "vocr_tc_conv3x3_wgrad_workspace_size": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
@@ -62,11 +65,11 @@ PROTOTYPES = {
     "vocr_split_f16_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_p]),
     "vocr_im2col3x3_f16": (c_int, [c_p, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
     "vocr_tc_gemm_f16x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p,
-                                   c_int, c_p, c_int, c_int, c_p, c_sz, c_p]),
+                                   c_int, c_p, c_int, c_int, c_p, c_sz, c_int, c_p]),
     "vocr_tc_conv3x3_fwd_f16": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
-                                        c_p]),
+                                        c_int, c_p]),
     "vocr_tc_conv3x3_wgrad_f16": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p,
-                                          c_sz, c_p]),
+                                          c_sz, c_int, c_p]),
 }
 
 _lib = None
@@ -77,8 +80,8 @@ KERNELS_PER_CALL = {
     "vocr_greedy_decode_f32": 2, "vocr_ctc_loss_f32": 4, "vocr_gemm_f32": 1, "vocr_colsum_f32": 1,
     "vocr_conv_weight_layout_f32": 1, "vocr_conv3x3_fwd_f32": 1, "vocr_conv3x3_wgrad_f32": 2, "vocr_rds_fwd_f32": 1,
     "vocr_rds_unpool_f32": 1, "vocr_rds_wgrad_c1_f32": 2, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
-    "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 1, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
-    "vocr_clamp_adam_f32": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
+    "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 4, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
+    "vocr_clamp_adam_f32": 1, "vocr_dropout_f32": 1, "vocr_rng_advance": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
     "vocr_split_f16_f32": 2, "vocr_im2col3x3_f16": 2, "vocr_tc_gemm_f16x3": 1, "vocr_tc_conv3x3_fwd_f16": 1, "vocr_tc_conv3x3_wgrad_f16": 2,
     "vocr_tc_conv3x3_fwd": 1, "vocr_tc_conv3x3_wgrad": 2, "vocr_colstats_f32": 1, "vocr_collate_lines_f32": 2, "vocr_scale_lines_u8": 1, "vocr_lm_frontend_f32": 1, "vocr_edit_distance_i32": 1,
 }
@@ -103,6 +106,7 @@ WORK = {
     "vocr_greedy_decode_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3]),
     "vocr_ctc_loss_f32": lambda a: ("byte", 8.0 * a[5] * a[6] * a[7]),
     "vocr_clamp_adam_f32": lambda a: ("byte", 28.0 * a[4]),
+    "vocr_dropout_f32": lambda a: ("byte", 8.0 * a[2]),
 }
 
 

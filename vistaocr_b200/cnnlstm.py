@@ -8,7 +8,7 @@ Same keyword-only constructor, attributes, `forward(x[B,C,H,W], widths[B]) -> (l
 calls them - every stage runs through vistaocr_b200.ops.  Differences, all deliberate:
   * the model always runs on the GPU (there is no CPU code path) and the whole model is one replica per process:
     `multigpu` is accepted but nn.DataParallel is never applied (data parallelism is one process per GPU + NCCL,
-    vistaocr_b200/dp.py); checkpoints written by a DataParallel model (`cnn.module.N.*` keys) still load;
+    vistaocr_b200/optim.py::FlatGradReducer + sharding.py); checkpoints written by a DataParallel model (`cnn.module.N.*` keys) still load;
   * LM decoding (`init_lm`, `decode_with_lm*`, needs the external EESEN decoder) is out of scope and raises.
 """
 import logging
@@ -54,6 +54,10 @@ class CnnOcrModel(nn.Module):
         if len(args) > 0:
             raise Exception("Only keyword arguments allowed in CnnOcrModel")
         self.hyper_params = kwargs.copy()
+        # this model never wraps `cnn` in nn.DataParallel, so its state_dict carries `cnn.N.*` keys: record that in the
+        # hyper-parameters a snapshot stores, or the reference's FromSavedWeights (strict=True) would rebuild a
+        # DataParallel model expecting `cnn.module.N.*` (reference cnnlstm.py:40-71,198-199)
+        self.hyper_params["multigpu"] = False
         self.input_line_height = kwargs["input_line_height"]
         self.rds_line_height = kwargs["rds_line_height"]
         self.alphabet = kwargs["alphabet"]
@@ -181,17 +185,41 @@ class CnnOcrModel(nn.Module):
         lens_dev = lens_cpu.to(x.device, non_blocking=True)
         seq = seq[:tmax]
         hid = self.num_lstm_hidden_units
+        dropping = self.training and self.p_lstm_dropout > 0
+        masks = getattr(self, "_dropout_masks", None)  # injected keep masks [L-1] x uint8 [T',B,2H] (parity tests)
+        bound = None
         for l in range(self.num_lstm_layers):
             g = lambda n: getattr(self.lstm, n % l)
             w_ih = torch.cat([g("weight_ih_l%d"), g("weight_ih_l%d_reverse")], 0)
             w_hh = torch.stack([g("weight_hh_l%d"), g("weight_hh_l%d_reverse")], 0)
             bias = torch.cat([g("bias_ih_l%d") + g("bias_hh_l%d"), g("bias_ih_l%d_reverse") + g("bias_hh_l%d_reverse")])
-            seq = ops.bilstm_layer(seq, w_ih, w_hh, bias, lens_dev, tmax, save=torch.is_grad_enabled())
-            if self.training and self.p_lstm_dropout > 0 and l < self.num_lstm_layers - 1:
-                seq = torch.nn.functional.dropout(seq, self.p_lstm_dropout, True)
+            seq = ops.bilstm_layer(seq, w_ih, w_hh, bias, lens_dev, tmax, save=torch.is_grad_enabled(), x_bound=bound)
+            bound = ops.const_scalar(x.device, 1.0)  # |h| = |o tanh(c)| < 1
+            if dropping and l < self.num_lstm_layers - 1:
+                # nn.LSTM(dropout=p) (reference cnnlstm.py:148-149): between layers, training only
+                if masks is not None:
+                    seq = ops.dropout(seq, self.p_lstm_dropout, mask=masks[l])
+                else:
+                    seq = ops.dropout(seq, self.p_lstm_dropout, rng=self._rng_state(x.device), site=l)
+                bound = ops.const_scalar(x.device, 1.0 / (1.0 - self.p_lstm_dropout))
+        if dropping and masks is None and self.num_lstm_layers > 1:
+            ops.rng_advance(self._rng_state(x.device), self.num_lstm_layers - 1)
         prob = self.prob_layer[0]
         logits = ops.linear(seq.reshape(tmax * b, 2 * hid), prob.weight, prob.bias).view(tmax, b, -1)
         return logits, lens_cpu
+
+    # ---- inter-layer dropout stream ---------------------------------------------------------------------------------
+    def _rng_state(self, device):
+        st = getattr(self, "_dropout_rng", None)
+        if st is None or st.device != device:
+            st = self._dropout_rng = ops.new_rng_state(device)
+        return st
+
+    def set_dropout_seed(self, seed, offset=0):
+        """Pin the Philox stream of the inter-layer dropout: the next training forward uses offsets `offset + l` for the
+        output of LSTM layer l (ops.dropout_keep_mask reproduces the masks), and advances the offset by L-1."""
+        dev = next(self.parameters()).device
+        self._dropout_rng = ops.new_rng_state(dev, seed, offset)
 
     # ---- greedy decode (reference cnnlstm.py:479-541 == decoder.py:116-185) --------------------------------------
     def decode_without_lm(self, model_output, batch_actual_timesteps, uxxxx=False):

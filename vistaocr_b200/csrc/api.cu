@@ -18,12 +18,17 @@ extern "C" const char* vocr_status_string(int status) {
 //   3 (default)  three error-compensated products per k-step: fp32-level accuracy (1e-5)
 //   1            one product on the hi planes: fp16 operands (11-bit mantissa, per-tensor power-of-two scaling),
 //                fp32 accumulation - the reduced-precision mode of BASELINE.json's cfg3 ("bf16 training")
+// Every entry point takes the mode PER CALL (`products`: 3, 1, or 0 = this process-wide default), so two models / two
+// threads of one process can run different modes without sharing mutable state on the launch path.
 namespace vocr {
-int g_tc_products = 3;
+std::atomic<int> g_tc_products{3};
+int resolve_tc_products(int products) {
+  return products == 0 ? g_tc_products.load(std::memory_order_relaxed) : products;
+}
 }
 extern "C" int vocr_set_tc_products(int n) {
   if (n != 1 && n != 3) return VOCR_INVALID_VALUE;
-  vocr::g_tc_products = n;
+  vocr::g_tc_products.store(n, std::memory_order_relaxed);
   return VOCR_OK;
 }
-extern "C" int vocr_get_tc_products(void) { return vocr::g_tc_products; }
+extern "C" int vocr_get_tc_products(void) { return vocr::g_tc_products.load(std::memory_order_relaxed); }

@@ -16,7 +16,25 @@
     if (!(cond)) return VOCR_INVALID_VALUE;  \
   } while (0)
 
+#include <atomic>
+
 namespace vocr {
+
+// cudaFuncSetAttribute is PER DEVICE: a process that drives several GPUs through this ABI must set the attributes once
+// on each of them.  One latch per call site; bit d = done on device d (setting twice from two threads is harmless).
+struct DeviceLatch {
+  std::atomic<unsigned long long> done[4];
+  bool need() const {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) return true;
+    return ((done[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1ull) == 0;
+  }
+  void set() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) return;
+    done[d >> 6].fetch_or(1ull << (d & 63), std::memory_order_release);
+  }
+};
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr float kNegInf = -INFINITY;

@@ -1016,14 +1016,14 @@ extern "C" int vocr_ctc_loss_f32(const float* acts, float* grads, const int32_t*
                    (grads == nullptr || reinterpret_cast<uintptr_t>(grads) % 16 == 0);
   const dim3 grid_rows((unsigned)B, (unsigned)ceil_div(max(T, 1), frames_per_cta));
   VOCR_REQUIRE(grid_rows.y <= 65535u);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceLatch attr_latch;
+  if (attr_latch.need()) {
     if (cudaFuncSetAttribute(ctc_lattice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(ctc_lattice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(ctc_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(ctc_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
-    attr_set = true;
+    attr_latch.set();
   }
   if (n_rows > 0) {
     if (vec)

@@ -3,8 +3,7 @@
 //   alpha = (in - 2) / (out - 1)  (fp32),  start_i = int((i + u) * alpha) - int(u * alpha)  for i < out-1,
 //   start_{out-1} = in - 2,       u = samples[n, c, 0] for W and samples[n, c, 1] for H.
 // The max scans the 2x2 window in (h, w) order with ATen's `val > max || isnan(val)` rule; the flat input index
-// (h*W + w) of the winner is kept for the backward scatter.  Windows overlap along W, so backward is an atomic
-// scatter-add.
+// (h*W + w) of the winner is kept for the backward scatter (deterministic, see fracpool_bwd_kernel).
 #include "common.cuh"
 
 namespace vocr {
@@ -47,17 +46,28 @@ fracpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ sampl
   }
 }
 
+// Backward: windows overlap (along W by one column whenever the start advances by 1), so the gradient is a scatter with
+// collisions.  ATen resolves them with atomicAdd (run-to-run order, non-deterministic sums once three or more windows
+// meet); here the scatter runs as FOUR passes over the (ho parity, wo parity) classes of the output: windows i and i+2
+// of one axis never overlap (starts strictly increase), so inside a pass every input element is touched by at most
+// one window and a plain read-modify-write is race free; the passes are stream ordered, i.e. the summation order is
+// fixed: deterministic gradients, no atomics.
 __global__ void __launch_bounds__(256)
-fracpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx, float* __restrict__ dx, int B,
-                    int HW, int C, int HoWo) {
-  // grid = (chunks of HoWo*C, B): 32-bit index arithmetic inside a sample
-  const int b = blockIdx.y;
-  const unsigned per = (unsigned)HoWo * (unsigned)C;
-  const size_t o0 = (size_t)b * per;
+fracpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx, float* __restrict__ dx, int HW, int C,
+                    int Ho, int Wo, int ph, int pw) {
+  // grid = (chunks of a row's selected windows x C, selected rows, B): 32-bit index arithmetic inside a sample
+  const int b = blockIdx.z;
+  const int ho = 2 * (int)blockIdx.y + ph;
+  const unsigned nw = (unsigned)((Wo - pw + 1) >> 1);  // windows of this row in the pass: wo = pw, pw+2, ...
+  const unsigned per = nw * (unsigned)C;
+  const size_t o0 = ((size_t)b * Ho + ho) * (size_t)Wo * C;
   float* dxb = dx + (size_t)b * HW * C;
   for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
-    const unsigned c = q % (unsigned)C;
-    atomicAdd(dxb + (size_t)__ldg(idx + o0 + q) * C + c, __ldg(dy + o0 + q));
+    const unsigned j = q / (unsigned)C;
+    const unsigned c = q - j * (unsigned)C;
+    const size_t o = o0 + (size_t)(2 * j + pw) * C + c;
+    float* d = dxb + (size_t)__ldg(idx + o) * C + c;
+    *d += __ldg(dy + o);
   }
 }
 
@@ -88,9 +98,14 @@ extern "C" int vocr_fracpool_bwd_f32(const float* dy, const int32_t* idx, float*
   const long long total = (long long)B * Ho * Wo * C;
   if (total == 0) return VOCR_OK;
   VOCR_REQUIRE(dy && idx);
-  VOCR_REQUIRE((long long)Ho * Wo * C < (1ll << 31) && B <= 65535);
-  dim3 grid((unsigned)min((long long)kNumSMs * 4, ceil_div64((long long)Ho * Wo * C, 256)), (unsigned)B);
-  fracpool_bwd_kernel<<<grid, 256, 0, stream>>>(dy, idx, dx, B, H * W, C, Ho * Wo);
-  VOCR_CHECK_LAUNCH();
+  VOCR_REQUIRE((long long)Ho * Wo * C < (1ll << 31) && B <= 65535 && Ho <= 2 * 65535);
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const int rows = (Ho - ph + 1) / 2, nw = (Wo - pw + 1) / 2;
+      if (rows <= 0 || nw <= 0) continue;
+      dim3 grid((unsigned)min(16ll, ceil_div64((long long)nw * C, 256)), (unsigned)rows, (unsigned)B);
+      fracpool_bwd_kernel<<<grid, 256, 0, stream>>>(dy, idx, dx, H * W, C, Ho, Wo, ph, pw);
+      VOCR_CHECK_LAUNCH();
+    }
   return VOCR_OK;
 }

@@ -6,7 +6,8 @@
 
 namespace vocr {
 
-extern int g_tc_products;  // api.cu: 3 = compensated products (default), 1 = hi planes only (vocr_set_tc_products)
+// api.cu: per-call arithmetic mode, 3 = compensated products, 1 = hi planes only, 0 = the vocr_set_tc_products default
+int resolve_tc_products(int products);
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(

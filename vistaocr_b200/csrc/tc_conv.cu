@@ -620,9 +620,10 @@ static void pick_tile(int H, int W, int* BW, int* BH) {
 template <bool F16>
 static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp_x, const void* w_hi, const void* w_lo,
                               const int* exp_w, const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
-                              cudaStream_t stream) {
+                              int products, cudaStream_t stream) {
   constexpr int CK = TcElem<F16>::kBK;
   VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % CK == 0 && Cout % 4 == 0);
+  VOCR_REQUIRE(products == 0 || products == 1 || products == 3);
   if (B == 0) return VOCR_OK;
   VOCR_REQUIRE(x_hi && x_lo && w_hi && w_lo && z && (!F16 || (exp_x && exp_w)));
   VOCR_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(z) &&
@@ -630,7 +631,7 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
   TcConvParams p;
   p.z = z; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.exp_x = exp_x; p.exp_w = exp_w;
-  p.single = (F16 && g_tc_products == 1) ? 1 : 0;
+  p.single = (F16 && resolve_tc_products(products) == 1) ? 1 : 0;
   pick_tile(H, W, &p.BW, &p.BH);
   p.tiles_x = ceil_div(W, p.BW);
   p.tiles_y = ceil_div(H, p.BH);
@@ -648,14 +649,14 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
          make_map_2d(&mw_hi, static_cast<const float*>(w_hi), Cout, 9LL * Cin, 9LL * Cin, CK, p.BN) &&
          make_map_2d(&mw_lo, static_cast<const float*>(w_lo), Cout, 9LL * Cin, 9LL * Cin, CK, p.BN);
   if (!ok) return VOCR_EXECUTION_FAILED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceLatch attr_latch;
+  if (attr_latch.need()) {
     if (cudaFuncSetAttribute(tc_conv_fwd_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) !=
             cudaSuccess ||
         cudaFuncSetAttribute(tc_conv_fwd_persist_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kCvSmemBytes) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
-    attr_set = true;
+    attr_latch.set();
   }
   const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
   const int n_tiles = ceil_div(Cout, p.BN);
@@ -677,14 +678,14 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
 extern "C" int vocr_tc_conv3x3_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                                    const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
                                    vocr_stream_t stream_) {
-  return tc_conv_fwd_launch<false>(x_hi, x_lo, nullptr, w_hi, w_lo, nullptr, bias, z, B, H, W, Cin, Cout,
+  return tc_conv_fwd_launch<false>(x_hi, x_lo, nullptr, w_hi, w_lo, nullptr, bias, z, B, H, W, Cin, Cout, 3,
                                    static_cast<cudaStream_t>(stream_));
 }
 extern "C" int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x,
                                        const uint16_t* w_hi, const uint16_t* w_lo, const int32_t* exp_w,
                                        const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
-                                       vocr_stream_t stream_) {
-  return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, z, B, H, W, Cin, Cout,
+                                       int products, vocr_stream_t stream_) {
+  return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, z, B, H, W, Cin, Cout, products,
                                   static_cast<cudaStream_t>(stream_));
 }
 
@@ -698,7 +699,7 @@ extern "C" size_t vocr_tc_conv3x3_wgrad_workspace_size(int B, int H, int W, int 
 template <bool F16>
 static int tc_conv_wgrad_launch(const void* x_hi, const void* x_lo, const int* exp_x, const void* dz_hi,
                                 const void* dz_lo, const int* exp_dz, float* dw, int B, int H, int W, int Cin,
-                                int Cout, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                int Cout, void* workspace, size_t workspace_bytes, int products, cudaStream_t stream) {
   using E = TcElem<F16>;
   constexpr int MB = E::kMnBox, PK = E::kBK;
   VOCR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % MB == 0 && Cout % MB == 0 && Cin > 0 && Cout > 0);
@@ -709,7 +710,8 @@ static int tc_conv_wgrad_launch(const void* x_hi, const void* x_lo, const int* e
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.M = 9 * Cin; p.N = Cout;
   p.exp_x = exp_x; p.exp_dz = exp_dz;
-  p.single = (F16 && g_tc_products == 1) ? 1 : 0;
+  VOCR_REQUIRE(products == 0 || products == 1 || products == 3);
+  p.single = (F16 && resolve_tc_products(products) == 1) ? 1 : 0;
   p.BN = (Cout <= 64) ? 64 : 128;
   p.xblocks = ceil_div(W, PK);
   const int tiles = ceil_div(p.M, 128) * ceil_div(p.N, p.BN);
@@ -729,12 +731,12 @@ static int tc_conv_wgrad_launch(const void* x_hi, const void* x_lo, const int* e
          make_map_nhwc(&md_hi, static_cast<const float*>(dz_hi), B, H, W, Cout, MB, PK, 1, true) &&
          make_map_nhwc(&md_lo, static_cast<const float*>(dz_lo), B, H, W, Cout, MB, PK, 1, true);
   if (!ok) return VOCR_EXECUTION_FAILED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceLatch attr_latch;
+  if (attr_latch.need()) {
     if (cudaFuncSetAttribute(tc_conv_wgrad_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes) !=
         cudaSuccess)
       return VOCR_EXECUTION_FAILED;
-    attr_set = true;
+    attr_latch.set();
   }
   dim3 grid(ceil_div(p.N, p.BN), ceil_div(p.M, 128), splits);
   tc_conv_wgrad_kernel<F16><<<grid, kCvThreads, kCvSmemBytes, stream>>>(mx_hi, mx_lo, md_hi, md_lo, p);
@@ -748,14 +750,14 @@ extern "C" int vocr_tc_conv3x3_wgrad(const float* x_hi, const float* x_lo, const
                                      float* dw, int B, int H, int W, int Cin, int Cout, void* workspace,
                                      size_t workspace_bytes, vocr_stream_t stream_) {
   return tc_conv_wgrad_launch<false>(x_hi, x_lo, nullptr, dz_hi, dz_lo, nullptr, dw, B, H, W, Cin, Cout, workspace,
-                                     workspace_bytes, static_cast<cudaStream_t>(stream_));
+                                     workspace_bytes, 3, static_cast<cudaStream_t>(stream_));
 }
 extern "C" int vocr_tc_conv3x3_wgrad_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x,
                                          const uint16_t* dz_hi, const uint16_t* dz_lo, const int32_t* exp_dz, float* dw,
                                          int B, int H, int W, int Cin, int Cout, void* workspace,
-                                         size_t workspace_bytes, vocr_stream_t stream_) {
+                                         size_t workspace_bytes, int products, vocr_stream_t stream_) {
   return tc_conv_wgrad_launch<true>(x_hi, x_lo, exp_x, dz_hi, dz_lo, exp_dz, dw, B, H, W, Cin, Cout, workspace,
-                                    workspace_bytes, static_cast<cudaStream_t>(stream_));
+                                    workspace_bytes, products, static_cast<cudaStream_t>(stream_));
 }
 
 // stats[0:C] += sum_p z[p,c], stats[C:2C] += sum_p z[p,c]^2 (float64).  C % 4 == 0, C <= 1024.

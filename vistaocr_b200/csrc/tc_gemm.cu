@@ -832,7 +832,8 @@ template <bool F16>
 static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a_hi, const void* a_lo, int lda,
                           const int* exp_a, const void* b_hi, const void* b_lo, int ldb, const int* exp_b, float* C,
                           int ldc, const float* bias, int relu, int accumulate, void* workspace,
-                          size_t workspace_bytes, cudaStream_t stream) {
+                          size_t workspace_bytes, int products, cudaStream_t stream) {
+  VOCR_REQUIRE(products == 0 || products == 1 || products == 3);
   using E = TcElem<F16>;
   constexpr int BK = E::kBK, ALIGN = F16 ? 8 : 4;
   VOCR_REQUIRE(M >= 0 && N >= 0 && K >= 1);
@@ -857,8 +858,8 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   else
     ok = ok && map2d(&mb_hi, b_hi, K, N, ldb, E::kMnBox, BK, true) && map2d(&mb_lo, b_lo, K, N, ldb, E::kMnBox, BK, true);
   if (!ok) return VOCR_EXECUTION_FAILED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceLatch attr_latch;
+  if (attr_latch.need()) {
     if (cudaFuncSetAttribute(tc_gemm_x3_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) !=
             cudaSuccess ||
         cudaFuncSetAttribute(tc_gemm_x3_shortk_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -866,7 +867,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
         cudaFuncSetAttribute(tc_gemm_x3_persist_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kTcSmemBytes) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
-    attr_set = true;
+    attr_latch.set();
   }
   const int tiles = ceil_div(N, kTcBN) * ceil_div(M, kTcBM);
   const int total_kb = ceil_div(K, BK);
@@ -880,7 +881,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   int kb_per_split = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kb_per_split);
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
-                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, (F16 && g_tc_products == 1) ? 1 : 0};
+                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, (F16 && resolve_tc_products(products) == 1) ? 1 : 0};
   dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
   if (splits == 1 && (total_kb <= kTcPersistMaxKb || p.single))
     tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(
@@ -904,7 +905,7 @@ extern "C" int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, cons
                                    const float* bias, int relu, int accumulate, void* workspace,
                                    size_t workspace_bytes, vocr_stream_t stream_) {
   return tc_gemm_launch<false>(a_mn, b_mn, M, N, K, a_hi, a_lo, lda, nullptr, b_hi, b_lo, ldb, nullptr, C, ldc, bias,
-                               relu, accumulate, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
+                               relu, accumulate, workspace, workspace_bytes, 3, static_cast<cudaStream_t>(stream_));
 }
 
 // Same GEMM on FP16 pair planes (vocr_split_f16_f32): planes hold op * 2^exp[0]; the epilogue undoes both scales.
@@ -912,7 +913,7 @@ extern "C" int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const
                                   const uint16_t* a_lo, int lda, const int32_t* exp_a, const uint16_t* b_hi,
                                   const uint16_t* b_lo, int ldb, const int32_t* exp_b, float* C, int ldc,
                                   const float* bias, int relu, int accumulate, void* workspace,
-                                  size_t workspace_bytes, vocr_stream_t stream_) {
+                                  size_t workspace_bytes, int products, vocr_stream_t stream_) {
   return tc_gemm_launch<true>(a_mn, b_mn, M, N, K, a_hi, a_lo, lda, exp_a, b_hi, b_lo, ldb, exp_b, C, ldc, bias, relu,
-                              accumulate, workspace, workspace_bytes, static_cast<cudaStream_t>(stream_));
+                              accumulate, workspace, workspace_bytes, products, static_cast<cudaStream_t>(stream_));
 }

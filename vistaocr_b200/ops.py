@@ -82,7 +82,7 @@ def tc_gemm16(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, bias=None, relu=False
     ws, wsb = _splitk_ws(M, N, K, C.device)
     st = lib().vocr_tc_gemm_f16x3(int(a_mn), int(b_mn), M, N, K, _off16(A[0], a_off), _off16(A[1], a_off), lda,
                                   ptr(A[2]), _off16(B[0], b_off), _off16(B[1], b_off), ldb, ptr(B[2]), _off(C, c_off),
-                                  ldc, ptr(bias), int(relu), int(accumulate), ptr(ws), wsb, stream())
+                                  ldc, ptr(bias), int(relu), int(accumulate), ptr(ws), wsb, _PRODUCTS[0], stream())
     check(st, "vocr_tc_gemm_f16x3")
 
 
@@ -109,22 +109,25 @@ USE_TC = _os.environ.get("VOCR_TC", "1") != "0"
 USE_F16 = USE_TC and _os.environ.get("VOCR_F16", "1") != "0"
 
 
+_PRODUCTS = [3]  # arithmetic mode handed to every tensor-core call of this module (per call, not library state)
+
+
 def set_precision(mode):
-    """Arithmetic of the tensor-core GEMM / convolution kernels, process-wide (vocr_set_tc_products):
+    """Arithmetic of the tensor-core GEMM / convolution kernels issued through this module (passed per call):
     "fp32" (default) - three error-compensated products on FP16 pair planes, results within 1e-5 of fp32 (cfg2);
     "fp16"           - one product on the hi planes: fp16 operands (11-bit mantissa, per-tensor power-of-two scaling),
                        fp32 accumulation, fp32 activations / master weights / optimiser - the reduced-precision
                        training mode of BASELINE.json's cfg3.  The BiLSTM recurrence keeps its compensated products.
     Returns the previous mode."""
-    prev = "fp16" if lib().vocr_get_tc_products() == 1 else "fp32"
+    prev = get_precision()
     if mode not in ("fp32", "fp16"):
         raise ValueError("precision must be 'fp32' or 'fp16'")
-    check(lib().vocr_set_tc_products(1 if mode == "fp16" else 3), "vocr_set_tc_products")
+    _PRODUCTS[0] = 1 if mode == "fp16" else 3
     return prev
 
 
 def get_precision():
-    return "fp16" if lib().vocr_get_tc_products() == 1 else "fp32"
+    return "fp16" if _PRODUCTS[0] == 1 else "fp32"
 
 
 class Operand:
@@ -262,7 +265,7 @@ def _tc_conv_fwd16(x_s, w_s, bias, B, H, W, Cin, Cout):
     """x_s, w_s: (hi, lo, state) FP16 pair planes; x NHWC [B,H,W,Cin], w K-major [Cout, 9*Cin]."""
     z = torch.empty((B, H, W, Cout), dtype=F32, device=x_s[0].device)
     st = lib().vocr_tc_conv3x3_fwd_f16(ptr(x_s[0]), ptr(x_s[1]), ptr(x_s[2]), ptr(w_s[0]), ptr(w_s[1]), ptr(w_s[2]),
-                                       ptr(bias), ptr(z), B, H, W, Cin, Cout, stream())
+                                       ptr(bias), ptr(z), B, H, W, Cin, Cout, _PRODUCTS[0], stream())
     check(st, "vocr_tc_conv3x3_fwd_f16")
     return z
 
@@ -273,7 +276,7 @@ def _tc_conv_wgrad16(x_s, dz_s, B, H, W, Cin, Cout):
     wsb = lib().vocr_tc_conv3x3_wgrad_workspace_size(B, H, W, Cin, Cout)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
     st = lib().vocr_tc_conv3x3_wgrad_f16(ptr(x_s[0]), ptr(x_s[1]), ptr(x_s[2]), ptr(dz_s[0]), ptr(dz_s[1]),
-                                         ptr(dz_s[2]), ptr(dw), B, H, W, Cin, Cout, ptr(ws), wsb, stream())
+                                         ptr(dz_s[2]), ptr(dw), B, H, W, Cin, Cout, ptr(ws), wsb, _PRODUCTS[0], stream())
     check(st, "vocr_tc_conv3x3_wgrad_f16")
     return dw
 
@@ -350,7 +353,8 @@ def conv3x3_wgrad(x, dz, x_op=None, dz_op=None):
         dz_op = dz_op or Operand(dz)
         return _tc_conv_wgrad16(x_op.split16(), dz_op.split16(), B, H, W, Cin, Cout)
     if USE_TC and Cin % 32 == 0 and Cout % 32 == 0:
-        x_op = x_op or Operand(x)
+        if x_op is None or (x_op.t is None and x_op._split is None):
+            x_op = Operand(x)  # a split-only operand that carries FP16 planes only: rebuild the TF32 planes from x
         dz_op = dz_op or Operand(dz)
         return _tc_conv_wgrad(x_op.split(), dz_op.split(), B, H, W, Cin, Cout)
     return _conv_wgrad(x, dz, B, H, W, Cin, Cout)
@@ -555,14 +559,14 @@ class _BiLSTMLayer(torch.autograd.Function):
     lens_dev int32 [B] on the device; tmax = max(lens) (python int).  Returns out [T,B,2H]."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, bias, lens_dev, tmax, save):
+    def forward(ctx, x, w_ih, w_hh, bias, lens_dev, tmax, save, x_bound=None):
         x, w_ih, w_hh, bias = _c(x), _c(w_ih), _c(w_hh), _c(bias)
         _lib.require_cuda(x, "x", F32)
         T, B, Din = x.shape
         H = w_hh.shape[2]
         dev = x.device
         xproj = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev)
-        xo, wo = Operand(x), Operand(w_ih)
+        xo, wo = Operand(x, bound=x_bound), Operand(w_ih)
         mm(0, 1, T * B, 8 * H, Din, xo, Din, wo, Din, xproj, 8 * H, bias=bias)
         out = torch.empty((T, B, 2 * H), dtype=F32, device=dev)
         gates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev) if save else None
@@ -597,7 +601,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         M = T * B
         xo, wo = ctx.ops
         ctx.ops = None
-        dgo, outo = Operand(dgates), Operand(out)
+        dgo, outo = Operand(dgates), Operand(out, bound=const_scalar(dev, 1.0))  # |h| < 1
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             mm(0, 0, M, Din, 8 * H, dgo, 8 * H, wo, Din, dx, Din)
@@ -616,11 +620,88 @@ class _BiLSTMLayer(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             db = torch.empty((8 * H,), dtype=F32, device=dev)
             colsum(dgates, M, 8 * H, 8 * H, db)
-        return dx, dw_ih, dw_hh, db, None, None, None
+        return dx, dw_ih, dw_hh, db, None, None, None, None
 
 
-def bilstm_layer(x, w_ih, w_hh, bias, lens_dev, tmax, save=True):
-    return _BiLSTMLayer.apply(x, w_ih, w_hh, bias, lens_dev, tmax, save)
+def bilstm_layer(x, w_ih, w_hh, bias, lens_dev, tmax, save=True, x_bound=None):
+    """x_bound: optional device scalar >= max|x| (the output of a previous layer is bounded by 1, or by 1/(1-p) after
+    dropout), which saves the operand split its absmax pass."""
+    return _BiLSTMLayer.apply(x, w_ih, w_hh, bias, lens_dev, tmax, save, x_bound)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# inter-layer LSTM dropout (reference nn.LSTM(dropout=p), cnnlstm.py:148-149)
+# ---------------------------------------------------------------------------------------------------------------
+_CONSTS = {}
+
+
+def const_scalar(device, value):
+    """A cached one-element fp32 device tensor (analytic operand bounds etc.)."""
+    key = (str(device), float(value))
+    t = _CONSTS.get(key)
+    if t is None:
+        t = _CONSTS[key] = torch.full((1,), float(value), dtype=F32, device=device)
+    return t
+
+
+def new_rng_state(device, seed=None, offset=0):
+    """Device-resident Philox state {seed, offset} (int64[2]); the seed defaults to a draw from torch's CPU generator,
+    so torch.manual_seed() makes dropout reproducible."""
+    if seed is None:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(offset)], dtype=torch.int64, device=device)
+
+
+def rng_advance(rng, inc):
+    check(lib().vocr_rng_advance(ptr(rng), int(inc), stream()), "vocr_rng_advance")
+
+
+def dropout_keep_mask(n, p, seed, offset, device):
+    """uint8[n] keep mask of the in-kernel Philox stream for (seed, offset) - what vocr_dropout_f32 applies."""
+    m = torch.empty((n,), dtype=torch.uint8, device=device)
+    st = lib().vocr_dropout_f32(None, None, n, float(p), None, int(seed), int(offset), None, None, ptr(m), stream())
+    check(st, "vocr_dropout_f32")
+    return m
+
+
+class _Dropout(torch.autograd.Function):
+    """y = x * keep / (1-p).  keep = `mask` (uint8, injected) or the Philox stream (rng state on the device + per-call
+    `site` offset); backward re-applies the same mask without ever storing it."""
+
+    @staticmethod
+    def forward(ctx, x, p, rng, site, mask):
+        x = _c(x)
+        _lib.require_cuda(x, "x", F32)
+        y = torch.empty_like(x)
+        used = None
+        if mask is not None:
+            mask = _c(mask.to(device=x.device, dtype=torch.uint8))
+            if mask.numel() != x.numel():
+                raise _lib.VocrError("dropout mask has %d elements, input has %d" % (mask.numel(), x.numel()))
+        else:
+            used = torch.empty((2,), dtype=torch.int64, device=x.device)
+        st = lib().vocr_dropout_f32(ptr(x), ptr(y), x.numel(), float(p), ptr(rng) if mask is None else None, 0,
+                                    int(site), ptr(used), ptr(mask), None, stream())
+        check(st, "vocr_dropout_f32")
+        ctx.p = float(p)
+        ctx.save_for_backward(used, mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        used, mask = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        st = lib().vocr_dropout_f32(ptr(dy), ptr(dx), dy.numel(), ctx.p, ptr(used), 0, 0, None, ptr(mask), None,
+                                    stream())
+        check(st, "vocr_dropout_f32")
+        return dx, None, None, None, None
+
+
+def dropout(x, p, rng=None, site=0, mask=None):
+    if mask is None and rng is None:
+        raise _lib.VocrError("dropout needs an rng state (ops.new_rng_state) or an injected mask")
+    return _Dropout.apply(x, p, rng, site, mask)
 
 
 # ---------------------------------------------------------------------------------------------------------------

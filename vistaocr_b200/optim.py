@@ -73,6 +73,12 @@ class FlatGradReducer:
                 self.gviews[i].copy_(p.grad)
                 p.grad = self.gviews[i]
             b = self.bucket_of[i]
+            if b in self.launched:
+                # a second backward before step() (gradient accumulation, retain_graph) would add local gradients into
+                # a buffer that is already reduced / in flight and the ranks would silently diverge
+                raise RuntimeError("FlatGradReducer: gradient of parameter %d arrived after its bucket was all-reduced; "
+                                   "overlap=True supports exactly one backward per optimizer.step() - construct "
+                                   "ClampAdam(..., overlap=False) to accumulate over several backward passes" % i)
             self.pending[b] -= 1
             if self.pending[b] == 0:
                 self._launch(b)
@@ -128,6 +134,39 @@ class ClampAdam(torch.optim.Optimizer):
     def flat_g(self):
         return self.reducer.flat_g
 
+    # ---- checkpointing: the reference snapshots `optimizer.state_dict()` (train_cnn_lstm.py:427-438) ---------------
+    def _views(self, flat):
+        plist = self.reducer.params
+        return [flat[o:o + p.numel()].view_as(p) for p, o in zip(plist, self.reducer.offsets)]
+
+    def state_dict(self):
+        """torch.optim.Adam's format (per-parameter `step`, `exp_avg`, `exp_avg_sq`), so a snapshot written here loads
+        into torch.optim.Adam and vice versa; the tensors are copies of the flat moment buffers."""
+        self.state.clear()
+        if self._step > 0:
+            for p, m, v in zip(self.reducer.params, self._views(self.flat_m), self._views(self.flat_v)):
+                self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        sd = super().state_dict()
+        self.state.clear()
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)  # validates groups / sizes, casts the tensors to the parameters' device
+        steps = set()
+        self.flat_m.zero_()
+        self.flat_v.zero_()
+        for p, m, v in zip(self.reducer.params, self._views(self.flat_m), self._views(self.flat_v)):
+            st = self.state.get(p)
+            if st:
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("ClampAdam keeps one step count for the whole flat buffer; the snapshot has %s" % sorted(steps))
+        self._step = steps.pop() if steps else 0
+        self.state.clear()
+
     def zero_grad(self, set_to_none=False):
         self.reducer.zero()
 
@@ -149,6 +188,8 @@ def broadcast_parameters(model, src=0, process_group=None):
 
 def train_step(batch, model, criterion, optimizer):
     """The reference's train() (src/train_cnn_lstm.py:131-150) on this package's model / loss / optimizer.
+    Data-parallel runs must give every rank the same number of steps (sharding.shard_batches(drop_last=True)): the
+    gradient all-reduce is a collective, a rank with one batch fewer would leave the others waiting in it.
     Returns the loss tensor (index [0] like the reference's `loss.data[0]`) without forcing a host sync."""
     input_tensor, target, input_widths, target_widths, metadata = batch
     input_tensor = input_tensor.cuda(non_blocking=True)

@@ -59,15 +59,41 @@ class _CTC(torch.autograd.Function):
         return g * go, None, None, None, None, None
 
 
+def count_infeasible(labels, act_lens, label_lens):
+    """Utterances no alignment exists for (act_len < label_len + number of adjacent repeated labels); host arithmetic
+    on the CPU tensors the reference passes (datautils.py:159-164).  Returns None when the inputs live on the device."""
+    if any(torch.is_tensor(t) and t.is_cuda for t in (labels, act_lens, label_lens)):
+        return None
+    import numpy as np
+    lab = torch.as_tensor(labels).numpy()
+    al, ll = torch.as_tensor(act_lens).numpy().astype(np.int64), torch.as_tensor(label_lens).numpy().astype(np.int64)
+    ends = np.cumsum(ll)
+    starts = ends - ll
+    eq = np.zeros(len(lab) + 1, np.int64)
+    if len(lab) > 1:
+        eq[1:len(lab)] = lab[1:] == lab[:-1]
+    eq[starts] = 0  # the first label of an utterance repeats nothing
+    cs = np.concatenate([[0], np.cumsum(eq[:len(lab)])])
+    rep = cs[ends] - cs[starts]
+    return int((al < ll + rep).sum())
+
+
 class CTCLoss(nn.Module):
     """host_cost=True returns the cost as a CPU FloatTensor[1] exactly like warp-ctc (one D2H sync);
-    host_cost=False keeps it on the device so the training step stays asynchronous."""
+    host_cost=False keeps it on the device so the training step stays asynchronous.
+    infeasible: what an utterance with no valid alignment contributes - "zero" (cost 0 / gradient 0, so one bad line
+    cannot poison a batch) or "inf" (the cost becomes +inf, gradient still 0: bad label / length data shows up in the
+    logged loss).  Either way `num_infeasible` holds the count for the last call (None for device-resident lengths)."""
 
-    def __init__(self, size_average=False, length_average=False, host_cost=True):
+    def __init__(self, size_average=False, length_average=False, host_cost=True, infeasible="zero"):
         super().__init__()
+        if infeasible not in ("zero", "inf"):
+            raise ValueError("infeasible must be 'zero' or 'inf'")
         self.size_average = size_average
         self.length_average = length_average
         self.host_cost = host_cost
+        self.infeasible = infeasible
+        self.num_infeasible = 0
 
     def forward(self, acts, labels, act_lens, label_lens):
         assert labels.dim() == 1 and act_lens.dim() == 1 and label_lens.dim() == 1
@@ -76,4 +102,8 @@ class CTCLoss(nn.Module):
             scale = 1.0 / float(torch.as_tensor(act_lens).sum().item())
         elif self.size_average:
             scale = 1.0 / acts.size(1)
-        return _CTC.apply(acts, labels, act_lens, label_lens, scale, self.host_cost)
+        self.num_infeasible = count_infeasible(labels, act_lens, label_lens)
+        loss = _CTC.apply(acts, labels, act_lens, label_lens, scale, self.host_cost)
+        if self.infeasible == "inf" and self.num_infeasible:
+            loss = loss + float("inf")
+        return loss
