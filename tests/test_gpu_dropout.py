@@ -106,13 +106,28 @@ def test_model_training_with_dropout_matches_oracle(cuda, mode):
     assert abs(loss.data[0].item() - wloss.item()) <= 2e-5 * abs(wloss.item())
     loss.backward()
     wloss.backward()
+    # the reference's own arithmetic (fp32) on the same masks: a ReLU / max-pool decision that sits within rounding of a
+    # tie flips between ANY two fp32 evaluations and moves a conv gradient by one term (~1e-3 of its max at this size),
+    # so the bound is "within 5e-4 / 5e-3 of float64, or no further from it than twice the fp32 oracle is"
+    sd32 = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in sd.items()}
+    w32, l32 = M.forward_ref(sd32, torch.from_numpy(x), widths, hp, (u1, u2), training=True, bn_updates={},
+                             dropout_masks=[m.float() for m in masks64], use_nn_lstm=False)
+    M.ctc_sum_ref(w32, labels, l32, label_lens).backward()
+    num = na = nb = 0.0
     for k, p in model.named_parameters():
         if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
             continue
         w = sd64[k].grad
         rtol = 5e-3 if (k.startswith("rapid_ds.") or (k.startswith("cnn.") and int(k.split(".")[1]) <= 11)) else 5e-4
         e = (p.grad.double().cpu() - w).abs().max().item()
-        assert e <= rtol * w.abs().max().item() + 1e-6, (k, e, w.abs().max().item())
+        e32 = (sd32[k].grad.double() - w).abs().max().item()
+        assert e <= max(rtol * w.abs().max().item(), 2.0 * e32) + 1e-6, (k, e, e32, w.abs().max().item())
+        assert e <= 1e-2 * w.abs().max().item()
+        num += (p.grad.double().cpu() * w).sum().item()
+        na += (p.grad.double().cpu() ** 2).sum().item()
+        nb += (w ** 2).sum().item()
+    assert num / (na ** 0.5 * nb ** 0.5) >= 1.0 - 1e-6  # the whole gradient, normwise
     # eval mode ignores dropout entirely
     model.eval()
     with torch.no_grad():

@@ -1,0 +1,95 @@
+"""GPU: CUDA-graph replay (vistaocr_b200/graphs.py) is the SAME computation as the eager call sequence - parameters after
+several optimizer steps and decoded strings are bit-identical, including when a replay carries other line lengths /
+labels than the batch the graph was captured on, and with the in-kernel dropout stream advancing inside the graph."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as M
+
+pytestmark = pytest.mark.gpu
+HP = dict(input_line_height=30, rds_line_height=30, lstm_input_dim=16, num_lstm_layers=3, num_lstm_hidden_units=24)
+A, B = 19, 4
+
+
+def _alphabet():
+    from vistaocr_b200 import Alphabet
+    return Alphabet(["<ctc-blank>"] + ["u%04x" % (0x61 + i) for i in range(A - 1)])
+
+
+def _model(p, seed=31):
+    from vistaocr_b200 import CnnOcrModel
+    hp = dict(HP, p_lstm_dropout=p)
+    m = CnnOcrModel(alphabet=_alphabet(), verbose=False, **hp)
+    m.load_state_dict(M.make_state_dict(hp, A, seed=seed), strict=True)
+    rng = np.random.default_rng(5)
+    m.cnn[6]._random_samples = torch.from_numpy(rng.random((B, 64, 2)).astype(np.float32))
+    m.cnn[13]._random_samples = torch.from_numpy(rng.random((B, 128, 2)).astype(np.float32))
+    return m
+
+
+def _batches():
+    """Two geometries; the second batch of each geometry shares the padded width, the longest line and the longest
+    labelling with the first but differs in every other length, label and pixel."""
+    rng = np.random.default_rng(17)
+    out = []
+    for wmax, lmax in ((150, 9), (97, 6)):
+        for variant in range(2):
+            widths = np.sort(np.concatenate([[wmax], rng.integers(40, wmax, size=B - 1)]))[::-1].astype(np.int32).copy()
+            x = np.zeros((B, 1, 30, wmax), np.float32)
+            for b in range(B):
+                x[b, :, :, :widths[b]] = rng.random((1, 30, widths[b]), dtype=np.float32)
+            ll = np.concatenate([[lmax], rng.integers(1, lmax + 1, size=B - 1)]).astype(np.int32)
+            rng.shuffle(ll)
+            ll = np.minimum(ll, [M.out_hw(30, int(w), 0)[1] // 2 for w in widths]).astype(np.int32)
+            ll[int(np.argmax(widths))] = lmax
+            lab = rng.integers(1, A, size=int(ll.sum())).astype(np.int32)
+            out.append((torch.from_numpy(x), torch.from_numpy(lab), torch.from_numpy(widths), torch.from_numpy(ll), {}))
+    return [out[0], out[2], out[1], out[3], out[0], out[3], out[1], out[2]]
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+def test_graphed_train_step_is_bit_identical_to_eager(cuda, p):
+    from vistaocr_b200 import ClampAdam, CTCLoss, GraphedTrainStep, train_step
+    seq = _batches()
+    ma, mb = _model(p), _model(p)
+    for m in (ma, mb):
+        m.train()
+        if p > 0:
+            m.set_dropout_seed(777, 0)
+    oa, ob = ClampAdam(ma.parameters(), lr=1e-2), ClampAdam(mb.parameters(), lr=1e-2)
+    ca, cb = CTCLoss(host_cost=False), CTCLoss(host_cost=False)
+    step = GraphedTrainStep(mb, cb, ob, capture_after=1)
+    la, lb = [], []
+    for b in seq:
+        la.append(train_step(b, ma, ca, oa)[0].item())
+        lb.append(step(b)[0].item())
+    assert step.graphs.captures == 2 and step.graphs.eager_calls == 2 and step.graphs.replays == len(seq) - 2
+    assert la == lb, (la, lb)
+    for (k, x), (_, y) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        assert torch.equal(x, y), k
+    assert all(np.isfinite(la)) and len(set(la)) == len(la)
+    if p > 0:
+        assert ma._dropout_rng.tolist() == mb._dropout_rng.tolist() == [777, 2 * len(seq)]
+    # the host-side checks still run on a replay
+    bad = (seq[0][0], seq[0][1], torch.flip(seq[0][2], [0]), seq[0][3], {})
+    with pytest.raises(RuntimeError):
+        step(bad)
+
+
+def test_graphed_decoder_matches_eager_strings(cuda):
+    from vistaocr_b200 import GraphedDecoder
+    m = _model(0.5)
+    m.eval()
+    dec = GraphedDecoder(m, capture_after=1)
+    seq = _batches()
+    for i, b in enumerate(seq):
+        x = b[0].pin_memory() if i % 2 else b[0].to(cuda)
+        got = dec(x, b[2], uxxxx=True)
+        with torch.no_grad():
+            logits, lens = m(b[0].to(cuda), b[2])
+        want = m.decode_without_lm(logits, lens, uxxxx=True)
+        assert got == want, i
+    assert dec.graphs.captures == 2 and dec.graphs.replays == len(seq) - 2
+    m.train()
+    assert dec.labels(seq[0][0].to(cuda), seq[0][2]) is None  # graphs are for the eval path only

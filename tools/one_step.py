@@ -8,11 +8,11 @@ from vistaocr_b200 import Alphabet, ClampAdam, CnnOcrModel, CTCLoss, train_step
 
 dev = torch.device("cuda:0")
 torch.manual_seed(7)
-alphabet = Alphabet(["<ctc-blank>"] + ["u%04x" % (0x21 + i) for i in range(bench.N_SYMBOLS - 1)])
-model = CnnOcrModel(alphabet=alphabet, verbose=False, **bench.CFG)
+alphabet = Alphabet(["<ctc-blank>"] + ["u%04x" % (0x21 + i) for i in range(bench.TRAIN["train_cfg2"]["n_symbols"] - 1)])
+model = CnnOcrModel(alphabet=alphabet, verbose=False, **bench.TRAIN["train_cfg2"]["hp"])
 model.train()
 crit, opt = CTCLoss(host_cost=False), ClampAdam(model.parameters(), lr=1e-3)
-host = bench.synth_batches(1000, 1)
+host = bench.synth_train_batches(bench.TRAIN["train_cfg2"], 1000, 1)
 res = [(b[0].to(dev), b[1].to(dev), b[2], b[3], b[4]) for b in host]
 for i in range(int(os.environ.get("WARM", 3)) + int(os.environ.get("STEPS", 1))):
     train_step(res[0], model, crit, opt)

@@ -6,6 +6,7 @@ from .warpctc import CTCLoss  # noqa: F401
 from .cnnlstm import CnnOcrModel  # noqa: F401
 from .optim import ClampAdam, train_step  # noqa: F401
 from .ops import get_precision, set_precision  # noqa: F401
+from .graphs import GraphedDecoder, GraphedTrainStep  # noqa: F401
 
 __all__ = ["Alphabet", "ArgmaxDecoder", "CTCLoss", "CnnOcrModel", "ClampAdam", "train_step", "set_precision",
-           "get_precision"]
+           "get_precision", "GraphedTrainStep", "GraphedDecoder"]

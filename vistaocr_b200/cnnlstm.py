@@ -182,7 +182,10 @@ class CnnOcrModel(nn.Module):
             # pack_padded_sequence(enforce_sorted=True) raises in the reference as well
             raise RuntimeError("`actual_minibatch_widths` must be sorted in decreasing order")
         lens_cpu = torch.tensor(lens, dtype=torch.int32)
-        lens_dev = lens_cpu.to(x.device, non_blocking=True)
+        # (graphs.py replays this forward with other lengths of the same maximum: it supplies the device copy itself)
+        lens_dev = getattr(self, "_lens_dev_override", None)
+        if lens_dev is None:
+            lens_dev = lens_cpu.to(x.device, non_blocking=True)
         seq = seq[:tmax]
         hid = self.num_lstm_hidden_units
         dropping = self.training and self.p_lstm_dropout > 0

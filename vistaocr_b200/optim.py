@@ -36,6 +36,7 @@ class FlatGradReducer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.handles = []
+        self.capturing = False
         self.buckets = []  # (lo, hi, n_params) element ranges of flat_g, in the order backward completes them
         self.collectives = 0
         if self.world > 1:
@@ -69,6 +70,8 @@ class FlatGradReducer:
 
     def _make_hook(self, i):
         def hook(p):
+            if self.capturing:  # CUDA-graph capture (graphs.py): the exchange runs after the replay, in finish()
+                return
             if p.grad is not self.gviews[i]:  # someone replaced .grad (zero_grad(set_to_none=True)): fold it back
                 self.gviews[i].copy_(p.grad)
                 p.grad = self.gviews[i]

@@ -11,14 +11,18 @@ import torch.nn as nn
 from . import _lib
 
 
-def ctc_costs_and_grads(acts, labels, act_lens, label_lens, want_grads=True):
-    """Device part: returns (costs[B] fp32 CUDA, grads[T,B,A] fp32 CUDA or None).  No host sync."""
+def ctc_costs_and_grads(acts, labels, act_lens, label_lens, want_grads=True, max_label_len=None):
+    """Device part: returns (costs[B] fp32 CUDA, grads[T,B,A] fp32 CUDA or None).  No host sync (device-resident
+    label lengths need `max_label_len`, an upper bound of the longest labelling, to size the workspace without one)."""
     _lib.require_cuda(acts, "acts", torch.float32)
     T, B, A = acts.shape
     dev = acts.device
     label_lens_h = torch.as_tensor(label_lens).to(torch.int32).cpu() if not torch.is_tensor(label_lens) or \
         not label_lens.is_cuda else None
-    if label_lens_h is not None:
+    if max_label_len is not None and label_lens_h is None:
+        max_l = int(max_label_len)
+        label_lens_d = label_lens.to(torch.int32)
+    elif label_lens_h is not None:
         max_l = int(label_lens_h.max().item()) if label_lens_h.numel() else 0
         label_lens_d = label_lens_h.to(dev, non_blocking=True)
     else:  # already on the device: one sync to size the workspace
@@ -42,9 +46,10 @@ def ctc_costs_and_grads(acts, labels, act_lens, label_lens, want_grads=True):
 
 class _CTC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, acts, labels, act_lens, label_lens, scale, host_cost):
+    def forward(ctx, acts, labels, act_lens, label_lens, scale, host_cost, max_label_len=None):
         acts_c = acts.detach().contiguous()
-        costs, grads = ctc_costs_and_grads(acts_c, labels, act_lens, label_lens, want_grads=acts.requires_grad)
+        costs, grads = ctc_costs_and_grads(acts_c, labels, act_lens, label_lens, want_grads=acts.requires_grad,
+                                           max_label_len=max_label_len)
         if grads is not None and scale != 1.0:
             grads.mul_(scale)
         ctx.grads = grads
@@ -56,7 +61,7 @@ class _CTC(torch.autograd.Function):
         g = ctx.grads
         ctx.grads = None
         go = grad_output.to(g.device, non_blocking=True).reshape(())
-        return g * go, None, None, None, None, None
+        return g * go, None, None, None, None, None, None
 
 
 def count_infeasible(labels, act_lens, label_lens):
