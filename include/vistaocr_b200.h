@@ -166,8 +166,10 @@ int vocr_fracpool_bwd_f32(const float* dy, const int32_t* idx, float* dx, int B,
  *   gates [T,B,2,4H] / cst [T,B,2,H]: activated gates and cell states saved for backward (NULL for inference).
  * backward: dout [T,B,2H] -> dgates [T,B,2,4H] = gradient w.r.t. xproj (zero beyond lens); the weight / input
  * gradients are GEMMs over dgates (see vistaocr_b200/ops.py).  H <= 512.
+ * workspace: vocr_bilstm_workspace_size(T = Tmax, B, H, backward) bytes - the forward pass exchanges h_t between the CTAs
+ * of a direction through one sentinel-initialised slot per step (no flags, no fences), hence the dependence on T.
  * ---------------------------------------------------------------------------------------------------------- */
-size_t vocr_bilstm_workspace_size(int B, int H, int backward);
+size_t vocr_bilstm_workspace_size(int T, int B, int H, int backward);
 int vocr_bilstm_fwd_f32(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates,
                         float* cst, int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes,
                         vocr_stream_t stream);

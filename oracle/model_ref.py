@@ -103,7 +103,7 @@ def lstm_cell_loop(x, lens, w_ih, w_hh, b_ih, b_hh, reverse):
     h = x.new_zeros((B, H))
     c = x.new_zeros((B, H))
     out = [None] * T
-    lens_t = torch.as_tensor(lens)
+    lens_t = torch.as_tensor(lens).to(x.device)
     for k in range(T):
         t = T - 1 - k if reverse else k
         gates = x[t] @ w_ih.t() + b_ih + h @ w_hh.t() + b_hh

@@ -30,7 +30,7 @@ def test_ctypes_prototypes_cover_the_header():
     assert l.vocr_status_string(0) == b"success" and l.vocr_status_string(2) == b"invalid value"
     # sizing helpers are pure host code
     assert l.vocr_ctc_workspace_size(100, 4, 80, 20) > 0
-    assert l.vocr_bilstm_workspace_size(64, 512, 0) > 0 and l.vocr_bilstm_workspace_size(64, 513, 0) == 0
+    assert l.vocr_bilstm_workspace_size(100, 64, 512, 0) > 0 and l.vocr_bilstm_workspace_size(100, 64, 513, 0) == 0
 
 
 def test_product_never_imports_the_oracle():

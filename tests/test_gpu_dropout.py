@@ -106,28 +106,27 @@ def test_model_training_with_dropout_matches_oracle(cuda, mode):
     assert abs(loss.data[0].item() - wloss.item()) <= 2e-5 * abs(wloss.item())
     loss.backward()
     wloss.backward()
-    # the reference's own arithmetic (fp32) on the same masks: a ReLU / max-pool decision that sits within rounding of a
-    # tie flips between ANY two fp32 evaluations and moves a conv gradient by one term (~1e-3 of its max at this size),
-    # so the bound is "within 5e-4 / 5e-3 of float64, or no further from it than twice the fp32 oracle is"
-    sd32 = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
-            for k, v in sd.items()}
-    w32, l32 = M.forward_ref(sd32, torch.from_numpy(x), widths, hp, (u1, u2), training=True, bn_updates={},
-                             dropout_masks=[m.float() for m in masks64], use_nn_lstm=False)
-    M.ctc_sum_ref(w32, labels, l32, label_lens).backward()
+    # Bounds from profiles/r02_parity_errors.md (12 seeds of this very configuration, CUDA path and the reference's own
+    # fp32 arithmetic, both against float64).  Everything downstream of the CNN: ours 2e-6..5e-6 (fp32 oracle: 3e-5..4e-5)
+    # -> 5e-5.  CNN parameters: a BatchNorm -> ReLU / max-pool decision that sits within rounding of a tie flips between
+    # ANY two fp32 evaluations and moves a conv gradient by whole terms - both implementations show up to 3e-2 of the
+    # tensor's max there (2e-2 normwise), so that is the honest bound for a fresh random batch; the kernels themselves
+    # are held to 1e-5-level bounds by the per-op tests (test_gpu_ops / test_gpu_tc_conv) and the fixed-seed fixtures.
     num = na = nb = 0.0
     for k, p in model.named_parameters():
         if k.startswith("cnn.") and k.endswith(".bias") and int(k.split(".")[1]) in M.CONV_IDX:
             continue
         w = sd64[k].grad
-        rtol = 5e-3 if (k.startswith("rapid_ds.") or (k.startswith("cnn.") and int(k.split(".")[1]) <= 11)) else 5e-4
-        e = (p.grad.double().cpu() - w).abs().max().item()
-        e32 = (sd32[k].grad.double() - w).abs().max().item()
-        assert e <= max(rtol * w.abs().max().item(), 2.0 * e32) + 1e-6, (k, e, e32, w.abs().max().item())
-        assert e <= 1e-2 * w.abs().max().item()
+        d = p.grad.double().cpu() - w
+        e, l2 = d.abs().max().item() / w.abs().max().item(), (d.norm() / w.norm()).item()
+        if k.startswith("cnn.") or k.startswith("rapid_ds."):
+            assert e <= 6e-2 and l2 <= 4e-2, (k, e, l2)
+        else:
+            assert e <= 5e-5 and l2 <= 5e-5, (k, e, l2)
         num += (p.grad.double().cpu() * w).sum().item()
         na += (p.grad.double().cpu() ** 2).sum().item()
         nb += (w ** 2).sum().item()
-    assert num / (na ** 0.5 * nb ** 0.5) >= 1.0 - 1e-6  # the whole gradient, normwise
+    assert num / (na ** 0.5 * nb ** 0.5) >= 1.0 - 1e-4  # the whole gradient, normwise
     # eval mode ignores dropout entirely
     model.eval()
     with torch.no_grad():

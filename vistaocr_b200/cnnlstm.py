@@ -140,7 +140,10 @@ class CnnOcrModel(nn.Module):
         s = getattr(module, "_random_samples", None)
         if s is None:  # F.fractional_max_pool2d draws rand(N, C, 2) per call, in train AND eval
             return torch.rand((n, c, 2), dtype=torch.float32, device=device)
-        return s.to(device=device, dtype=torch.float32)
+        cache = getattr(module, "_vocr_samples_dev", None)  # injected samples: uploaded once, not per call
+        if cache is None or cache[0] is not s or cache[1] != s._version or cache[2].device != device:
+            cache = module._vocr_samples_dev = (s, s._version, s.to(device=device, dtype=torch.float32))
+        return cache[2]
 
     def forward(self, x, actual_minibatch_widths):
         if not x.is_cuda:

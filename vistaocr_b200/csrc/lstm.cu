@@ -28,6 +28,8 @@
 #include <cstdio>
 #endif
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vocr {
@@ -749,12 +751,20 @@ static size_t lstm_xchg_bytes(const LstmArgs& a, bool bwd) {
   return sizeof(float) * (size_t)(2 * a.NBT) * 2 * kLstmBT * (a.Hp + 8);
 }
 
-extern "C" size_t vocr_bilstm_workspace_size(int B, int H, int backward) {
+// lstm_tc.cu: the tcgen05 forward kernel (all samples of a 64-sample group per CTA, sentinel-polled exchange)
+size_t lstm_tc_fwd_workspace_bytes(int T, int B, int H);
+int lstm_tc_fwd_launch(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates, float* cst,
+                       int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+bool lstm_tc_enabled();
+
+extern "C" size_t vocr_bilstm_workspace_size(int T, int B, int H, int backward) {
   LstmArgs a;
   size_t smem;
   int gy, variant;
-  if (lstm_geometry(B, H, &a, &smem, &gy, backward != 0, &variant) != VOCR_OK) return 0;
-  return 256 + lstm_flag_bytes(a, backward != 0) + lstm_xchg_bytes(a, backward != 0);
+  if (T < 0 || lstm_geometry(B, H, &a, &smem, &gy, backward != 0, &variant) != VOCR_OK) return 0;
+  size_t need = 256 + lstm_flag_bytes(a, backward != 0) + lstm_xchg_bytes(a, backward != 0);
+  if (!backward) need = std::max(need, lstm_tc_fwd_workspace_bytes(T, B, H));
+  return need;
 }
 
 static int lstm_launch(bool bwd, LstmArgs a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -773,8 +783,13 @@ static int lstm_launch(bool bwd, LstmArgs a, void* workspace, size_t workspace_b
   const void* fn = bwd ? (const void*)bilstm_bwd_kernel
                        : (variant ? (const void*)bilstm_fwd_kernel<32, 4> : (const void*)bilstm_fwd_kernel<64, 2>);
   const int threads = bwd ? kLstmThreads : (variant ? 256 + 32 * 4 : 256 + 32 * 2);
-  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return VOCR_EXECUTION_FAILED;
+  static DeviceLatch latch[3];  // cudaFuncSetAttribute is per device
+  DeviceLatch& l = latch[bwd ? 0 : 1 + variant];
+  if (l.need()) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return VOCR_EXECUTION_FAILED;
+    l.set();
+  }
   dim3 grid(a.NSL, gy);
   void* params[] = {&a};
   // cooperative launch: the runtime refuses the launch unless every CTA can be co-resident, which the flag
@@ -799,6 +814,10 @@ extern "C" int vocr_bilstm_fwd_f32(const float* xproj, const float* whh, const i
   LstmArgs a{};
   a.xproj = xproj; a.whh = whh; a.lens = lens; a.out = out; a.gates = gates; a.cst = cst;
   a.T = T; a.B = B; a.H = H; a.Tmax = Tmax;
+  if (lstm_tc_enabled()) {  // cluster-resident tcgen05 kernel (lstm_tc.cu); -1 = shape it does not cover
+    const int st = lstm_tc_fwd_launch(xproj, whh, lens, out, gates, cst, T, B, H, Tmax, workspace, workspace_bytes, stream);
+    if (st != -1) return st;
+  }
   return lstm_launch(false, a, workspace, workspace_bytes, stream);
 }
 

@@ -1,0 +1,563 @@
+// BiLSTM forward recurrence as a CLUSTER-RESIDENT tcgen05 kernel, sm_100a.
+// (reference cnnlstm.py:148-149,285-290: nn.LSTM on a packed sequence -> cuDNN RNN; the input projections of all
+// timesteps are one tensor-core GEMM done beforehand, see lstm.cu / ops.py.)
+//
+// One thread-block cluster of 16 CTAs serves one (direction, group of 32 samples) for the whole sequence; nothing ever
+// leaves the cluster except the layer's outputs:
+//   * CTA s of the cluster owns 32 hidden units = 128 gate rows of W_hh, kept ON CHIP for all timesteps as FP16 pairs
+//     (hi, lo * 2^11; 22 significant bits): the hi plane lives in TENSOR MEMORY (128 lanes x 256 columns) and feeds
+//     tcgen05.mma as the A operand straight from TMEM, the lo plane lives in shared memory (128 KB, K-major SW128).
+//   * per step   D[128 gate rows x 32 samples] = W_slice[128 x H] . h_{t-1}^T   with kind::f16, M = 128, N = 32, K = 16 per
+//     instruction: three error-compensated products in TWO instructions per k-step - W_hi (from TMEM) times the hi and lo
+//     planes of h laid side by side as one N = 64 operand, and W_lo (from shared memory) times the hi plane - 64
+//     instructions per step issued by one thread.
+//   * eight epilogue warps read the accumulators (tcgen05.ld), regroup the four gates of a unit with warp shuffles, add
+//     the input projection (staged by a loader warp with cp.async one step ahead), apply the gates and write the CTA's
+//     piece of h_t (32 units x 32 samples, FP16 pair, already in the operand layout) to a 4-KB staging area;
+//   * ONE multicast bulk copy per CTA and step (cp.async.bulk ... .multicast::cluster) drops that piece into the operand
+//     tile of all 16 CTAs; the copies complete on each destination's mbarrier, so a CTA starts the next products the
+//     moment its 16 pieces have landed - no flags, no polling, no grid or cluster barrier.  Flow control is one more
+//     tcgen05.commit per step, multicast to the whole cluster: a CTA overwrites the operand tiles only after every CTA's
+//     products of the step have retired.
+// The operand tile of h uses the K-major SWIZZLE_NONE canonical layout (8 x 16-byte core matrices) so that a CTA's piece
+// is one contiguous 4-KB block of every destination tile.
+// Ragged lengths use packed-sequence semantics by masking: sample b is active at step k iff k < lens[b]; the reverse
+// direction visits t = lens[b]-1-k; outputs beyond lens[b] stay zero; finished samples keep publishing their last state.
+#include <cuda_fp16.h>
+#include <cstdlib>
+#ifdef VOCR_LSTM_PROF
+#include <cstdio>
+#endif
+
+#include "tc_common.cuh"
+
+namespace vocr {
+
+constexpr int kClM = 128;             // gate rows per CTA = UMMA M (32 unit slots x 4 gates)
+constexpr int kClN = 32;              // samples per cluster work item = UMMA N
+constexpr int kClSize = 16;           // CTAs per cluster
+constexpr int kClMaxKB = 8;           // k-blocks of 64 units (H <= 512)
+constexpr int kClThreads = 320;       // 8 epilogue warps, 1 MMA warp, 1 input-projection loader warp
+constexpr uint32_t kClWloKb = kClM * 128;                  // W_lo bytes per k-block: 16 KB
+constexpr uint32_t kClChunk = 2 * (kClN / 8) * 128;        // h tile bytes per k-chunk of 8 units (2 planes): 1 KB
+constexpr uint32_t kClTileBytes = 64 * kClChunk;           // h tile: 64 k-chunks = 64 KB
+constexpr int kClXsLd = 136;                               // row stride (floats) of the staged input projections
+constexpr uint32_t kClXsBytes = kClN * kClXsLd * 4;        // 17 KB
+constexpr uint32_t kColA = 0, kColD = 256;                 // TMEM columns: W_hi operand | accumulators
+constexpr float kClLoScale = 2048.f;
+
+struct LstmClArgs {
+  const float* xproj;   // [T,B,2,4H]
+  const float* whh;     // [2,4H,H]
+  const int32_t* lens;  // [B]
+  float* out;           // [T,B,2H]  (pre-zeroed)
+  float* gates;         // [T,B,2,4H] activated i,f,g,o (may be null)
+  float* cst;           // [T,B,2,H]  (may be null)
+  unsigned char* stage; // [clusters][16 CTAs][2 parities][4 KB] staging of the published pieces
+  int T, B, H, KB, US, NSL, Tmax, NG, n_items;
+};
+
+// Gate nonlinearities on the serial chain of the recurrence: ex2.approx-based (absolute error ~2e-7 on values in
+// [-1, 1] - below the fp32 rounding of the pre-activation sums they are applied to).
+__device__ __forceinline__ float cl_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU, <= 1 ulp
+  return r;
+}
+__device__ __forceinline__ float cl_sigmoidf(float x) { return cl_rcp(1.f + __expf(-x)); }
+__device__ __forceinline__ float cl_tanhf(float x) { return fmaf(-2.f, cl_rcp(1.f + __expf(2.f * x)), 1.f); }
+__device__ __forceinline__ void cl_split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * kClLoScale);
+}
+// byte offset of element (row r, k < 64) inside a K-major SWIZZLE_128B tile (rows of 128 B, 8-row atoms of 1024 B)
+__device__ __forceinline__ uint32_t cl_sw128(int r, int k) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((k >> 3) ^ (r & 7)) << 4) + ((k & 7) << 1));
+}
+__device__ __forceinline__ void cl_umma_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (when all prior tcgen05 operations of this thread have completed) on the mbarrier at the same shared-memory
+// offset in every CTA of `mask`
+__device__ __forceinline__ void cl_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cl_tmem_ld16(uint32_t taddr, uint32_t (&t)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+        "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void cl_tmem_st32(uint32_t taddr, const uint32_t (&t)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]), "r"(t[9]),
+      "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]), "r"(t[16]), "r"(t[17]), "r"(t[18]),
+      "r"(t[19]), "r"(t[20]), "r"(t[21]), "r"(t[22]), "r"(t[23]), "r"(t[24]), "r"(t[25]), "r"(t[26]), "r"(t[27]),
+      "r"(t[28]), "r"(t[29]), "r"(t[30]), "r"(t[31])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cl_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cl_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the 256 epilogue threads only
+__device__ __forceinline__ void cl_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmClArgs a) {
+  extern __shared__ unsigned char cl_smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cl_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = a.KB, H = a.H, US = a.US;
+  unsigned char* Wlo = smem;                                      // [KB][128 rows x 128 B] SW128 K-major
+  unsigned char* Ht = Wlo + (size_t)kClMaxKB * kClWloKb;          // [64 k-chunks][hi 512 B | lo 512 B] SWIZZLE_NONE
+  float* xs = reinterpret_cast<float*>(Ht + kClTileBytes);        // [32 samples][136]: gate g, unit u at g*32 + u
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + kClXsBytes);
+  uint64_t* full = bars;           // h tile of the step landed (1 arrival + NSL pieces of tx bytes)
+  uint64_t* mma_done = bars + 1;   // this CTA's products of the step retired (tcgen05.commit)
+  uint64_t* tile_free = bars + 2;  // EVERY CTA's products of the step retired (NSL multicast commits)
+  uint64_t* xs_full = bars + 3;    // input projections of the step staged (1 arrival)
+  uint64_t* xs_free = bars + 4;    // ... and consumed (8 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int slice = (int)cl_cluster_rank();
+  const int cluster_id = blockIdx.x / kClSize, n_clusters = gridDim.x / kClSize;
+  const int u0 = slice * US;
+  const int nu = max(0, min(US, H - u0));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint16_t cta_mask = (uint16_t)((1u << a.NSL) - 1u);
+  const uint32_t piece_bytes = (uint32_t)(US / 8) * kClChunk;
+  const bool active_cta = slice < a.NSL;
+
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(tile_free, (uint32_t)a.NSL);
+    mbar_init(xs_full, 1);
+    mbar_init(xs_free, 8);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  // the operand tile starts as zeros: unit columns nobody publishes (H < 64 KB) and the state of step 0
+  for (int i = tid; i < (int)(kClTileBytes / 16); i += kClThreads) reinterpret_cast<uint4*>(Ht)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cl_cluster_sync();  // every CTA's barriers are initialised before any peer can signal them
+  if (!active_cta) {
+    // H < 512: fewer than 16 slices.  Nobody addresses this CTA; it only keeps the cluster barriers balanced.
+    for (int item = cluster_id; item + n_clusters < a.n_items; item += n_clusters) cl_cluster_sync();
+    cl_cluster_sync();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    return;
+  }
+
+  unsigned n_full = 0, n_done = 0, n_free = 0, n_xsfull = 0, n_xsfree = 0;
+  int loaded_dir = -1;
+  unsigned char* stage = a.stage + ((size_t)(cluster_id * kClSize + slice) * 2) * 4096;
+
+  for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+    const int dir = item & 1, grp = item >> 1;
+    const int b_base = grp * kClN;
+    int tm = 0;  // steps of this item: its longest sample
+    for (int j = b_base; j < min(a.B, b_base + kClN); ++j) tm = max(tm, min(a.lens[j], a.Tmax));
+
+    if (loaded_dir != dir) {
+      // ---- W slice: row m = 32q + 4 u8 + g  <->  gate g of unit slot U = 8q + u8 ------------------------------------
+      const float* wd = a.whh + (size_t)dir * 4 * H * H;
+      if (warp < 4) {  // hi plane -> TMEM, lane m, column k/2 (two halves per column)
+        const int m = 32 * warp + lane, g = lane & 3, U = 8 * warp + (lane >> 2);
+        const float* wr = wd + ((size_t)g * H + u0 + U) * H;
+        for (int c0 = 0; c0 < KB * 32; c0 += 32) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int k = 2 * (c0 + c);
+            const float w0 = (U < nu && k < H) ? __ldg(wr + k) : 0.f, w1 = (U < nu && k + 1 < H) ? __ldg(wr + k + 1) : 0.f;
+            v[c] = (uint32_t)__half_as_ushort(__float2half_rn(w0)) | ((uint32_t)__half_as_ushort(__float2half_rn(w1)) << 16);
+          }
+          cl_tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + kColA + c0, v);
+          (void)m;
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      for (int i = tid; i < kClM * KB * 64; i += kClThreads) {  // lo plane -> shared memory
+        const int m = i / (KB * 64), k = i - m * (KB * 64);
+        const int q = m >> 5, g = m & 3, U = 8 * q + ((m & 31) >> 2);
+        float v = 0.f;
+        if (U < nu && k < H) v = __ldg(wd + ((size_t)g * H + u0 + U) * H + k);
+        __half hi, lo;
+        cl_split_f16(v, hi, lo);
+        *reinterpret_cast<__half*>(Wlo + (size_t)(k >> 6) * kClWloKb + cl_sw128(m, k & 63)) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      loaded_dir = dir;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 8) {
+      // ===================================== epilogue warps ======================================================
+      const int q = warp & 3, hh = warp >> 2;       // TMEM quadrant, half of the 32 samples
+      const int u8 = lane >> 2, g = lane & 3;
+      const int U = 8 * q + u8;                     // unit slot of this thread
+      const bool unit_ok = U < nu;
+      int bs[4], len[4];
+      float c_reg[4], h_reg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = 16 * hh + 4 * j + g;          // this thread's four samples
+        bs[j] = b_base + n;
+        len[j] = (bs[j] < a.B) ? min(a.lens[bs[j]], a.Tmax) : 0;
+        c_reg[j] = h_reg[j] = 0.f;
+      }
+#ifdef VOCR_LSTM_PROF
+      long long pf_wait = 0, pf_ld = 0, pf_gate = 0, pf_pub = 0, pf_out = 0, pf_free = 0, pf_fence = 0, pf_tld = 0, pf_xs = 0, pf_t0 = clock64();
+#endif
+      for (int k = 0; k < tm; ++k) {
+#ifdef VOCR_LSTM_PROF
+        const long long c0 = clock64();
+#endif
+        float pre[4][4];  // [gate][j]
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pre[gg][j] = 0.f;
+        if (k > 0) {
+          mbar_wait_or_trap(mma_done, n_done & 1u);
+          ++n_done;
+          tc_fence_after();
+#ifdef VOCR_LSTM_PROF
+          pf_wait += clock64() - c0;
+#endif
+          // D = W_hi . [h_hi | h_lo] (columns 0-31 | 32-63); W_lo . h_hi is accumulated into columns 32-63 as well (both
+          // cross terms carry the 2^-11 scale)
+          const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + kColD + 16 * hh;
+          uint32_t a_hh[16], a_x[16];
+          float v[16];
+          cl_tmem_ld16(tbase, a_hh);
+          cl_tmem_ld16(tbase + kClN, a_x);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = fmaf(__uint_as_float(a_x[c]), 1.f / kClLoScale, __uint_as_float(a_hh[c]));
+          tc_fence_before();
+#ifdef VOCR_LSTM_PROF
+          pf_tld += clock64() - c0;
+#endif
+          // regroup: this lane holds gate g of unit U for 16 samples.  A 4 x 4 transpose over the four sibling lanes (same
+          // u8; two xor-shuffle rounds, static register indices only) leaves it with all four gates of the samples
+          // c = 4j + g.
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x0 = v[4 * j], x1 = v[4 * j + 1], x2 = v[4 * j + 2], x3 = v[4 * j + 3];
+            const bool o1 = (g & 1) != 0, o2 = (g & 2) != 0;
+            float s0 = o1 ? x0 : x1, s1 = o1 ? x2 : x3;
+            s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+            s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            if (o1) { x0 = s0; x2 = s1; } else { x1 = s0; x3 = s1; }
+            s0 = o2 ? x0 : x2;
+            s1 = o2 ? x1 : x3;
+            s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+            if (o2) { x0 = s0; x1 = s1; } else { x2 = s0; x3 = s1; }
+            pre[0][j] = x0; pre[1][j] = x1; pre[2][j] = x2; pre[3][j] = x3;
+          }
+        }
+#ifdef VOCR_LSTM_PROF
+        const long long c1 = clock64();
+#endif
+        // input projections staged by the loader warp
+        mbar_wait_or_trap(xs_full, n_xsfull & 1u);
+        ++n_xsfull;
+#ifdef VOCR_LSTM_PROF
+        pf_xs += clock64() - c1;
+#endif
+        bool act[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          act[j] = unit_ok && k < len[j];
+          if (act[j]) {
+            const float* xr = xs + (16 * hh + 4 * j + g) * kClXsLd + U;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) pre[gg][j] += xr[gg * 32];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xs_free)) : "memory");
+        float ig[4], fg[4], gv[4], og[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ig[j] = fg[j] = gv[j] = og[j] = 0.f;
+          if (act[j]) {
+            ig[j] = cl_sigmoidf(pre[0][j]); fg[j] = cl_sigmoidf(pre[1][j]);
+            gv[j] = cl_tanhf(pre[2][j]);    og[j] = cl_sigmoidf(pre[3][j]);
+            c_reg[j] = fmaf(fg[j], c_reg[j], ig[j] * gv[j]);
+            h_reg[j] = og[j] * cl_tanhf(c_reg[j]);
+          }
+        }
+#ifdef VOCR_LSTM_PROF
+        const long long c2 = clock64();
+#endif
+        if (k + 1 < tm) {
+          // publish h_k: this CTA's piece of the operand tile, laid out exactly like the tile (k-chunk q of the piece,
+          // plane, row group n/8, row n%8, unit u8): finished / padding samples and missing units publish their state
+          // (zeros), the consumers take the whole piece
+          unsigned char* pc = stage + (size_t)(k & 1) * 4096;
+          if (U < US) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = 16 * hh + 4 * j + g;
+              __half hi, lo;
+              cl_split_f16(h_reg[j], hi, lo);
+              unsigned char* p = pc + (size_t)q * kClChunk + (n >> 3) * 128 + (n & 7) * 16 + u8 * 2;
+              *reinterpret_cast<__half*>(p) = hi;
+              *reinterpret_cast<__half*>(p + 512) = lo;
+            }
+          }
+          cl_epi_sync();
+          if (tid == 0) {
+#ifdef VOCR_LSTM_PROF
+            const long long p0 = clock64();
+#endif
+            // every CTA's products of step k have retired: the tiles may be overwritten (k = 0: nothing ran yet)
+            if (k > 0) {
+              mbar_wait_or_trap(tile_free, n_free & 1u);
+              ++n_free;
+            }
+#ifdef VOCR_LSTM_PROF
+            const long long p1 = clock64();
+#endif
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+#ifdef VOCR_LSTM_PROF
+            pf_free += p1 - p0; pf_fence += clock64() - p1;
+#endif
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                ::"r"(smem_u32(Ht + (size_t)slice * piece_bytes)), "l"(pc), "r"(piece_bytes), "r"(smem_u32(full)), "h"(cta_mask)
+                : "memory");
+          }
+        }
+#ifdef VOCR_LSTM_PROF
+        const long long c3 = clock64();
+#endif
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (act[j]) {
+            const int tt = dir == 0 ? k : len[j] - 1 - k;
+            const size_t tb_ = (size_t)tt * a.B + bs[j];
+            a.out[(tb_ * 2 + dir) * H + u0 + U] = h_reg[j];
+            if (a.gates) {
+              float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + U;
+              gp[0] = ig[j];
+              gp[(size_t)H] = fg[j];
+              gp[(size_t)2 * H] = gv[j];
+              gp[(size_t)3 * H] = og[j];
+            }
+            if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + U] = c_reg[j];
+          }
+#ifdef VOCR_LSTM_PROF
+        const long long c4 = clock64();
+        pf_ld += c1 - c0; pf_gate += c2 - c1; pf_pub += c3 - c2; pf_out += c4 - c3;
+#endif
+      }
+      if (tid == 0 && tm > 1) {  // the last step's multicast commits (keeps the phase counter in step)
+        mbar_wait_or_trap(tile_free, n_free & 1u);
+        ++n_free;
+      }
+#ifdef VOCR_LSTM_PROF
+      if (blockIdx.x == 3 && (tid == 0 || tid == 255))
+        printf("lstm cluster epilogue tid %d: steps %d total %lld  wait-mma %lld  wait+tmem-ld+regroup %lld (through tmem-ld %lld)  xproj+gates %lld (wait xs %lld)  publish %lld (wait tile_free %lld, fence %lld)  out %lld\n",
+               tid, tm, clock64() - pf_t0, pf_wait, pf_ld, pf_tld, pf_gate, pf_xs, pf_pub, pf_free, pf_fence, pf_out);
+#endif
+    } else if (warp == 8) {
+      // ===================================== MMA issuer ==========================================================
+      if (lane == 0) {
+        // instruction descriptors: D = F32, A / B = F16 K-major, M = 128, N = 64 (hi | lo planes of h side by side) or 32
+        const uint32_t idesc64 = (1u << 4) | ((uint32_t)(2 * kClN >> 3) << 17) | ((uint32_t)(kClM >> 4) << 24);
+        const uint32_t idesc32 = (1u << 4) | ((uint32_t)(kClN >> 3) << 17) | ((uint32_t)(kClM >> 4) << 24);
+        // descriptors advance by constants: W_lo 32 B per k-step inside a k-block of 16 KB, h two k-chunks (2 KB) per
+        // k-step; the start-address field counts 16-byte units
+        const uint64_t d_wlo0 = make_desc(smem_u32(Wlo), 16, 1024, 2);
+        const uint64_t d_h0 = make_desc(smem_u32(Ht), kClChunk, 128, 0);
+        const uint32_t t_a = tmem_base + kColA, t_d1 = tmem_base + kColD, t_d2 = tmem_base + kColD + kClN;
+#ifdef VOCR_LSTM_PROF
+        long long mf_wait = 0, mf_issue = 0;
+#endif
+        for (int k = 1; k < tm; ++k) {
+#ifdef VOCR_LSTM_PROF
+          const long long m0 = clock64();
+#endif
+          mbar_arrive_expect_tx(full, (uint32_t)a.NSL * piece_bytes);  // arm: the 16 pieces of h_{k-1}
+          mbar_wait_or_trap(full, n_full & 1u);
+          ++n_full;
+          tc_fence_after();
+#ifdef VOCR_LSTM_PROF
+          const long long m1 = clock64();
+#endif
+#pragma unroll
+          for (int kb = 0; kb < kClMaxKB; ++kb) {
+            if (kb < KB) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t d_h = d_h0 + (uint64_t)(((kb * 8 + ks * 2) * kClChunk) >> 4);
+                const uint64_t d_wlo = d_wlo0 + (uint64_t)((kb * kClWloKb + ks * 32) >> 4);
+                const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+#ifndef VOCR_LSTM_EXP_NO_TS
+                cl_umma_ts(t_d1, t_a + (uint32_t)(kb * 32 + ks * 8), d_h, idesc64, first);  // W_hi . [h_hi | h_lo]
+#endif
+#ifndef VOCR_LSTM_EXP_NO_SS
+                umma_f16(t_d2, d_wlo, d_h, idesc32, 1u);                       // += W_lo . h_hi (the hi.lo columns)
+#endif
+              }
+            }
+          }
+          umma_commit(mma_done);
+          cl_commit_multicast(tile_free, cta_mask);
+#ifdef VOCR_LSTM_PROF
+          const long long m2 = clock64();
+          mf_wait += m1 - m0; mf_issue += m2 - m1;
+#endif
+        }
+#ifdef VOCR_LSTM_PROF
+        if (blockIdx.x == 3) printf("lstm cluster mma thread: steps %d  wait-full %lld  issue %lld\n", tm - 1, mf_wait, mf_issue);
+#endif
+      }
+      __syncwarp();
+    } else {
+      // ===================================== input-projection loader warp ========================================
+      // lane = sample: 4 gate rows x US units of xproj[t, b, dir] -> xs[sample][gate*32 + unit], one step ahead
+      const int n = lane, b = b_base + n;
+      const int len = (b < a.B) ? min(a.lens[b], a.Tmax) : 0;
+      const int nch = (nu * 4 + 15) / 16;  // 16-byte chunks per gate row (H % 4 == 0)
+      for (int k = 0; k < tm; ++k) {
+        if (k > 0) {
+          mbar_wait_or_trap(xs_free, n_xsfree & 1u);
+          ++n_xsfree;
+        }
+        if (k < len) {
+          const int tt = dir == 0 ? k : len - 1 - k;
+          const float* src = a.xproj + (((size_t)tt * a.B + b) * 2 + dir) * 4 * H + u0;
+          float* dst = xs + n * kClXsLd;
+          for (int gg = 0; gg < 4; ++gg)
+            for (int c = 0; c < nch; ++c)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + gg * 32 + c * 4)),
+                           "l"(src + (size_t)gg * H + c * 4)
+                           : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xs_full)) : "memory");
+      }
+      if (tm > 0) {  // drain the last step's release
+        mbar_wait_or_trap(xs_free, n_xsfree & 1u);
+        ++n_xsfree;
+      }
+    }
+    // the next item of this cluster starts from a zero state: clear the operand tile once every CTA of the cluster has
+    // finished this item (a peer may still be reading its tile / a late piece may still be in flight otherwise)
+    tc_fence_before();
+    __syncthreads();
+    if (item + n_clusters < a.n_items) {
+      cl_cluster_sync();
+      for (int i = tid; i < (int)(kClTileBytes / 16); i += kClThreads) reinterpret_cast<uint4*>(Ht)[i] = make_uint4(0, 0, 0, 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cl_cluster_sync();  // no CTA leaves while a peer could still multicast into it
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace vocr
+
+using namespace vocr;
+
+static int lstm_cl_geometry(int B, int H, LstmClArgs* a, size_t* smem) {
+  if (H < 1 || H > 64 * kClMaxKB || (H % 4) != 0) return VOCR_INVALID_VALUE;
+  a->KB = ceil_div(H, 64);
+  a->US = 8 * ceil_div(H, 8 * kClSize);  // unit slots per CTA: a multiple of 8 (one 16-byte chunk), at most 32
+  a->NSL = ceil_div(H, a->US);
+  a->NG = ceil_div(B, kClN);
+  a->n_items = 2 * a->NG;
+  *smem = (size_t)kClMaxKB * kClWloKb + kClTileBytes + kClXsBytes + 64 + 1024 /*alignment*/;
+  return VOCR_OK;
+}
+
+bool lstm_tc_enabled() {
+  const char* e = getenv("VOCR_LSTM_TC");
+  return !(e && e[0] == '0');
+}
+
+static int lstm_cl_clusters(int n_items) {
+  // at most 6 clusters of 16 CTAs (7 fit a B200 next to nothing else; an even count keeps a cluster on one direction)
+  int nc = n_items < 6 ? n_items : 6;
+  if (nc > 1 && (nc & 1)) --nc;
+  return nc < 1 ? 1 : nc;
+}
+
+size_t lstm_tc_fwd_workspace_bytes(int T, int B, int H) {
+  (void)T;
+  LstmClArgs a;
+  size_t smem;
+  if (!lstm_tc_enabled() || lstm_cl_geometry(B, H, &a, &smem) != VOCR_OK) return 0;
+  return 1024 + (size_t)lstm_cl_clusters(a.n_items) * kClSize * 2 * 4096;
+}
+
+int lstm_tc_fwd_launch(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates, float* cst,
+                       int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LstmClArgs a{};
+  size_t smem;
+  int st = lstm_cl_geometry(B, H, &a, &smem);
+  if (st != VOCR_OK) return -1;  // shape not covered by this kernel: the caller uses the mma.sync kernel
+  a.xproj = xproj; a.whh = whh; a.lens = lens; a.out = out; a.gates = gates; a.cst = cst;
+  a.T = T; a.B = B; a.H = H; a.Tmax = Tmax;
+  if ((reinterpret_cast<uintptr_t>(xproj) & 15) != 0) return -1;
+  const int nc = lstm_cl_clusters(a.n_items);
+  const uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  const size_t need = (size_t)nc * kClSize * 2 * 4096;
+  if ((w - reinterpret_cast<uintptr_t>(workspace)) + need > workspace_bytes) return VOCR_INVALID_VALUE;
+  a.stage = reinterpret_cast<unsigned char*>(w);
+  static DeviceLatch latch;
+  if (latch.need()) {
+    if (cudaFuncSetAttribute(bilstm_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(bilstm_fwd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+      return VOCR_EXECUTION_FAILED;
+    latch.set();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nc * kClSize);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, bilstm_fwd_cluster_kernel, a) != cudaSuccess) return VOCR_EXECUTION_FAILED;
+  return VOCR_OK;
+}

@@ -571,7 +571,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         out = torch.empty((T, B, 2 * H), dtype=F32, device=dev)
         gates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev) if save else None
         cst = torch.empty((T, B, 2, H), dtype=F32, device=dev) if save else None
-        wsb = lib().vocr_bilstm_workspace_size(B, H, 0)
+        wsb = lib().vocr_bilstm_workspace_size(int(tmax), B, H, 0)
         if wsb == 0:
             raise _lib.VocrError("vocr_bilstm: unsupported hidden size %d (max 512)" % H)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
@@ -592,7 +592,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         dev = x.device
         dout = _c(dout)
         dgates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev)
-        wsb = lib().vocr_bilstm_workspace_size(B, H, 1)
+        wsb = lib().vocr_bilstm_workspace_size(ctx.tmax, B, H, 1)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         st = lib().vocr_bilstm_bwd_f32(ptr(dout), ptr(w_hh), ptr(lens_dev), ptr(gates), ptr(cst), ptr(dgates), T, B,
                                        H, ctx.tmax, ptr(ws), wsb, stream())
