@@ -77,6 +77,13 @@ def test_model_training_with_dropout_matches_oracle(cuda, mode):
     else:
         model.set_dropout_seed(4242, offset=10)
         keep = [keep_mask(n, 0.5, 4242, 10 + l).reshape(tmax, B, H2) for l in range(2)]
+    # eval mode ignores dropout entirely (checked first: the training forward below updates the running statistics)
+    model.eval()
+    with torch.no_grad():
+        ev, _ = model(torch.from_numpy(x).to(cuda), torch.from_numpy(widths))
+    sd64e = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    wev, _ = M.forward_ref(sd64e, torch.from_numpy(x).double(), widths, hp, (u1, u2), training=False, use_nn_lstm=False)
+    assert (ev.double().cpu() - wev.detach()).abs().max().item() <= 2e-5 * wev.abs().max().item() + 2e-6
     model.train()
     logits, olens = model(torch.from_numpy(x).to(cuda), torch.from_numpy(widths))
     if mode == "philox":
@@ -127,9 +134,3 @@ def test_model_training_with_dropout_matches_oracle(cuda, mode):
         na += (p.grad.double().cpu() ** 2).sum().item()
         nb += (w ** 2).sum().item()
     assert num / (na ** 0.5 * nb ** 0.5) >= 1.0 - 1e-4  # the whole gradient, normwise
-    # eval mode ignores dropout entirely
-    model.eval()
-    with torch.no_grad():
-        ev, _ = model(torch.from_numpy(x).to(cuda), torch.from_numpy(widths))
-    wev, _ = M.forward_ref(sd64, torch.from_numpy(x).double(), widths, hp, (u1, u2), training=False, use_nn_lstm=False)
-    assert (ev.double().cpu() - wev.detach()).abs().max().item() <= 2e-5 * wev.abs().max().item() + 2e-6
