@@ -290,7 +290,8 @@ def _full_size_against_oracle_on_gpu(cuda, tag, hp, A, B, wmin, wmax, seed, prec
 
 
 def _check_fp32_contract(rec):
-    """Bounds = 2x what profiles/r02_parity_errors.md records for these runs (tightened from round 1's 5e-5 / 2e-2)."""
+    """Logits / loss: the north-star 1e-5 (measured 2e-6..3e-6 / 6e-8..2e-7); gradients: within 2x of what
+    profiles/r02_parity_errors.md records for these runs (tightened from round 1's 5e-5 / 5e-5 / 2e-2)."""
     assert rec["logits_err_vs_f64"] <= LOGITS_FULL, rec["logits_err_vs_f64"]
     assert rec["loss_err_vs_f64"] <= LOSS_FULL, rec["loss_err_vs_f64"]
     worst = 0.0
@@ -300,10 +301,12 @@ def _check_fp32_contract(rec):
         # dominate the tensors upstream of a pool at this size), and within GRAD_FULL of the tensor scale otherwise
         assert e["ours"] <= max(GRAD_FULL, 2.0 * e["ref32"]) + 1e-9, (k, e)
     assert worst <= GRAD_FULL_WORST, worst
-    assert rec["grad_cosine"] >= 1.0 - 1e-6
+    assert rec["grad_cosine"] >= 1.0 - 5e-7
 
 
-LOGITS_FULL, LOSS_FULL, GRAD_FULL, GRAD_FULL_WORST = 5e-5, 5e-5, 1e-3, 2e-2
+# measured (profiles/r02_parity_errors.md): logits 1.9e-6 / 2.8e-6, loss 5.8e-8 / 1.5e-7, worst gradient tensor 2.3e-3 / 3.8e-3
+# (the fp32 oracle: 3.8e-3 / 5.1e-3).  Logits and loss are held to the north-star 1e-5.
+LOGITS_FULL, LOSS_FULL, GRAD_FULL, GRAD_FULL_WORST = 1e-5, 1e-5, 1e-3, 1e-2
 CFG2 = dict(input_line_height=60, rds_line_height=30, lstm_input_dim=128, num_lstm_layers=3,
             num_lstm_hidden_units=512, p_lstm_dropout=0.5)
 CFG3 = dict(input_line_height=120, rds_line_height=30, lstm_input_dim=128, num_lstm_layers=3,
@@ -331,9 +334,10 @@ def test_full_size_cfg3_reduced_precision_documented_bound(cuda):
     logits within 1e-2 of the float64 logits' scale, CTC loss within 1e-3 relative, and the full gradient within a
     cosine of 0.99 of the float64 gradient (measured values in profiles/r02_parity_errors.md)."""
     rec = _full_size_against_oracle_on_gpu(cuda, "cfg3", CFG3, 166, 64, 400, 2000, 78, "fp16")
+    # measured: logits 1.6e-3, loss 3.4e-6, cosine 1 - 7.5e-5
     assert rec["logits_err_vs_f64"] <= 1e-2, rec["logits_err_vs_f64"]
     assert rec["loss_err_vs_f64"] <= 1e-3, rec["loss_err_vs_f64"]
-    assert rec["grad_cosine"] >= 0.99, rec["grad_cosine"]
+    assert rec["grad_cosine"] >= 0.999, rec["grad_cosine"]
 
 
 def test_decode_testset_sequence_from_raw_images(cuda):

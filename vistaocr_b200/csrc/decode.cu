@@ -95,6 +95,10 @@ argmax_path_kernel(const float* __restrict__ logits, long long n_rows, int T, in
   }
   const int warp = threadIdx.x >> 5;
   const int sub = lane_id() / kLanesPerRow;
+  // (t, b) of the tile's first row once per CTA; rows inside the tile then need only a 32-bit division (the 64-bit
+  // division per row was a visible share of the instruction stream of this issue-bound kernel)
+  const int t0 = (int)(row0 / B);
+  const unsigned b0 = (unsigned)(row0 - (long long)t0 * B);
   for (int r0 = warp * kRowsPerWarpPass; r0 < rows_here; r0 += kDecWarps * kRowsPerWarpPass) {
     const int r = r0 + sub;
     const bool valid = r < rows_here;
@@ -102,8 +106,8 @@ argmax_path_kernel(const float* __restrict__ logits, long long n_rows, int T, in
     int mi;
     row_argmax8(rows + (size_t)r * A, valid, A, mv, mi);
     if (valid && (lane_id() & (kLanesPerRow - 1)) == 0) {
-      const long long gr = row0 + r;
-      const int t = (int)(gr / B), b = (int)(gr % B);
+      const unsigned br = b0 + (unsigned)r, dt = br / (unsigned)B;
+      const int t = t0 + (int)dt, b = (int)(br - dt * (unsigned)B);
       int label = -1;
       if (t < lens[b]) label = (mi == 0 || mv < thresh) ? 0 : mi;
       path[(size_t)b * T + t] = label;

@@ -511,9 +511,9 @@ bool lstm_tc_enabled() {
 }
 
 static int lstm_cl_clusters(int n_items) {
-  // at most 6 clusters of 16 CTAs (7 fit a B200 next to nothing else; an even count keeps a cluster on one direction)
-  int nc = n_items < 6 ? n_items : 6;
-  if (nc > 1 && (nc & 1)) --nc;
+  // at most 7 clusters of 16 CTAs are co-resident on a B200 (cudaOccupancyMaxActiveClusters at this footprint); with an
+  // odd count a cluster alternates between the directions and re-loads its W_hh slice per item (~1 % of an item)
+  const int nc = n_items < 7 ? n_items : 7;
   return nc < 1 ? 1 : nc;
 }
 
