@@ -129,8 +129,9 @@ int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const
  * vocr_bn_relu_bwd_f32: da (same strided layout) -> dz[B,H,W,C], dgamma, dbeta, dbias (= sum dz, the gradient of
  *   the conv bias in front of the BatchNorm; may be NULL).  red_ws: float64[3*C] scratch.
  * FP16 pair planes (see vocr_split_f16_f32) come out of the same kernels without an extra pass over the tensor:
- *   vocr_bn_finalize_f32 aux (device float[2], optional): [0] = an analytic upper bound of the activations (batch
- *     statistics only: |xhat| <= sqrt(count); 0 otherwise), [1] = max_c |scale_c|.
+ *   vocr_bn_finalize_f32 aux (device float[2], optional): [0] = an upper bound of the activations - analytic with batch
+ *     statistics (|xhat| <= sqrt(count)); with running statistics max_c(|scale_c| zmax + |shift_c|) when the conv's
+ *     measured zmax = max |z| is passed, 0 otherwise -, [1] = max_c |scale_c|.
  *   vocr_bn_relu_apply_f32 a_hi16 / a_lo16 / bound (= aux) / pair_exp (device int32, receives the exponent).
  *   vocr_bn_relu_bwd_f32 dz_hi16 / dz_lo16 / scale_max (= aux + 1) / pair_state (device int32[2]: [0] receives the
  *     exponent, [1] scratch); the bound max|scale| * max|g| * (2 + sqrt(N)) is formed on the device.
@@ -138,7 +139,7 @@ int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const
 int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, float momentum, float eps, int training,
                          float* scale, float* shift, float* save_mean, float* save_invstd, int C, float* aux,
-                         vocr_stream_t stream);
+                         const float* zmax, vocr_stream_t stream);
 int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, float* a_hi, float* a_lo,
                            int B, int H, int W, int C, long long sB, long long sH, long long sW, uint16_t* a_hi16,
                            uint16_t* a_lo16, const float* bound, int32_t* pair_exp, vocr_stream_t stream);
@@ -165,7 +166,8 @@ int vocr_fracpool_bwd_f32(const float* dy, const int32_t* idx, float* dx, int B,
  *   out [T,B,2H] (forward | reverse), zero for t >= lens[b];  Tmax = max(lens) <= T.
  *   gates [T,B,2,4H] / cst [T,B,2,H]: activated gates and cell states saved for backward (NULL for inference).
  * backward: dout [T,B,2H] -> dgates [T,B,2,4H] = gradient w.r.t. xproj (zero beyond lens); the weight / input
- * gradients are GEMMs over dgates (see vistaocr_b200/ops.py).  H <= 512.
+ * gradients are GEMMs over dgates (see vistaocr_b200/ops.py).  H <= 512.  dgates_absmax (device float, optional)
+ * receives max |dgates|: the operand bound of those GEMMs, so that their FP16-pair split needs no abs-max pass.
  * workspace: vocr_bilstm_workspace_size(T = Tmax, B, H, backward) bytes - the forward pass exchanges h_t between the CTAs
  * of a direction through one sentinel-initialised slot per step (no flags, no fences), hence the dependence on T.
  * ---------------------------------------------------------------------------------------------------------- */
@@ -174,8 +176,8 @@ int vocr_bilstm_fwd_f32(const float* xproj, const float* whh, const int32_t* len
                         float* cst, int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes,
                         vocr_stream_t stream);
 int vocr_bilstm_bwd_f32(const float* dout, const float* whh, const int32_t* lens, const float* gates,
-                        const float* cst, float* dgates, int T, int B, int H, int Tmax, void* workspace,
-                        size_t workspace_bytes, vocr_stream_t stream);
+                        const float* cst, float* dgates, float* dgates_absmax, int T, int B, int H, int Tmax,
+                        void* workspace, size_t workspace_bytes, vocr_stream_t stream);
 
 /* Inter-layer LSTM dropout (nn.LSTM(dropout=p), src/models/cnnlstm.py:148-149; p = 0.5 at src/train_cnn_lstm.py:331;
  * training only, on the output of every layer but the last).  y[i] = keep[i] ? x[i] * 1/(1-p) : 0 (in place allowed).
@@ -219,6 +221,9 @@ int vocr_tc_gemm_tf32x3(int a_mn, int b_mn, int M, int N, int K, const float* a_
  *   (when NULL an absmax pass computes it).  Everything stays on the stream - no host synchronisation.
  * vocr_tc_gemm_f16x3 / vocr_tc_conv3x3_fwd_f16 / vocr_tc_conv3x3_wgrad_f16: as their TF32 namesakes, taking the planes
  *   and the device exponent of each operand; lda / ldb multiples of 8, Cin % 64 == 0 (and Cout % 64 == 0 for wgrad).
+ *   zmax (vocr_tc_conv3x3_fwd_f16, optional device float the caller zeroes): the epilogue max-es |z| into it, which lets
+ *   vocr_bn_finalize_f32 bound the activations of an eval-mode block so that vocr_bn_relu_apply_f32 can write the next
+ *   layer's operand planes without an abs-max pass.
  *   products: arithmetic mode of THIS call - 3 = three compensated products (fp32-level), 1 = hi planes only (fp16
  *   operands, fp32 accumulation), 0 = the process default of vocr_set_tc_products.
  * ---------------------------------------------------------------------------------------------------------- */
@@ -235,7 +240,7 @@ int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const uint16_t* 
                        size_t workspace_bytes, int products, vocr_stream_t stream);
 int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* w_hi,
                             const uint16_t* w_lo, const int32_t* exp_w, const float* bias, float* z, int B, int H, int W,
-                            int Cin, int Cout, int products, vocr_stream_t stream);
+                            int Cin, int Cout, int products, float* zmax, vocr_stream_t stream);
 int vocr_tc_conv3x3_wgrad_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* dz_hi,
                               const uint16_t* dz_lo, const int32_t* exp_dz, float* dw, int B, int H, int W, int Cin,
                               int Cout, void* workspace, size_t workspace_bytes, int products, vocr_stream_t stream);

@@ -36,7 +36,7 @@ PROTOTYPES = {
     "vocr_rds_unpool_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
     "vocr_rds_wgrad_c1_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     "vocr_bn_finalize_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_f, c_f, c_int, c_p, c_p, c_p, c_p, c_int, c_p,
-                                     c_p]),
+                                     c_p, c_p]),
     "vocr_bn_relu_apply_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
                                        c_p, c_p, c_p, c_p, c_p]),
     "vocr_bn_relu_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll,
@@ -45,7 +45,7 @@ PROTOTYPES = {
     "vocr_fracpool_bwd_f32": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "vocr_bilstm_workspace_size": (c_sz, [c_int, c_int, c_int, c_int]),
     "vocr_bilstm_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
-    "vocr_bilstm_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
+    "vocr_bilstm_bwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_clamp_adam_f32": (c_int, [c_p, c_p, c_p, c_p, c_ll, c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
     "vocr_dropout_f32": (c_int, [c_p, c_p, c_ll, c_f, c_p, c_ull, c_ull, c_p, c_p, c_p, c_p]),
     "vocr_rng_advance": (c_int, [c_p, c_ull, c_p]),
@@ -67,7 +67,7 @@ PROTOTYPES = {
     "vocr_tc_gemm_f16x3": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_p, c_int, c_p, c_p,
                                    c_int, c_p, c_int, c_int, c_p, c_sz, c_int, c_p]),
     "vocr_tc_conv3x3_fwd_f16": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int,
-                                        c_int, c_p]),
+                                        c_int, c_p, c_p]),
     "vocr_tc_conv3x3_wgrad_f16": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p,
                                           c_sz, c_int, c_p]),
 }
@@ -102,7 +102,7 @@ WORK = {
     # (B*4H) and writes h (B*H) - backward: reads dout, the gates, c and writes the gate gradients (B*10H) - W_hh and the
     # running state stay on chip
     "vocr_bilstm_fwd_f32": lambda a: ("byte", 4.0 * a[9] * 2 * a[7] * 5 * a[8]),
-    "vocr_bilstm_bwd_f32": lambda a: ("byte", 4.0 * a[9] * 2 * a[7] * 10 * a[8]),
+    "vocr_bilstm_bwd_f32": lambda a: ("byte", 4.0 * a[10] * 2 * a[8] * 10 * a[9]),
     "vocr_greedy_decode_f32": lambda a: ("byte", 4.0 * a[1] * a[2] * a[3]),
     "vocr_ctc_loss_f32": lambda a: ("byte", 8.0 * a[5] * a[6] * a[7]),
     "vocr_clamp_adam_f32": lambda a: ("byte", 28.0 * a[4]),

@@ -173,7 +173,8 @@ class CnnOcrModel(nn.Module):
         hh, cc = self.cnn_out_h, self.cnn_out_c
         lin = self.bridge_layer[0]
         w_bridge = lin.weight.view(-1, cc, hh).permute(0, 2, 1).reshape(-1, hh * cc)
-        seq = ops.linear(feat.view(wf * b, hh * cc), w_bridge, lin.bias, relu=True).view(wf, b, -1)
+        seq = ops.linear(feat.view(wf * b, hh * cc), w_bridge, lin.bias, relu=True,
+                         x_bound=getattr(feat, "_vocr_bound", None)).view(wf, b, -1)
 
         widths = actual_minibatch_widths.tolist() if torch.is_tensor(actual_minibatch_widths) \
             else list(actual_minibatch_widths)

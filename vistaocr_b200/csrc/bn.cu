@@ -20,7 +20,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
                                    float* __restrict__ running_var, float momentum, float eps, int training,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int C,
-                                   unsigned* __restrict__ aux) {
+                                   unsigned* __restrict__ aux, const float* __restrict__ zmax) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, invstd;
@@ -49,7 +49,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
     // (one value cannot exceed the whole sum of squares).  Loose by ~2^9, which the FP16 pair format absorbs
     // (pair_f16.cuh).  Not available with running statistics (0 -> the consumer computes an absmax).
     // aux[1]: max_c |scale_c| (bounds the backward pass's dz).  Non-negative floats order like their bit patterns.
+    // With running statistics the bound comes from the convolution's measured max |z|: |a| <= |scale| zmax + |shift|.
     if (training) atomicMax(&aux[0], __float_as_uint(fabsf(gamma[c]) * sqrtf((float)count) + fabsf(beta[c])));
+    else if (zmax) atomicMax(&aux[0], __float_as_uint(fmaf(fabsf(sc), __ldg(zmax), fabsf(beta[c] - mean * sc))));
     atomicMax(&aux[1], __float_as_uint(fabsf(sc)));
   }
 }
@@ -263,7 +265,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 extern "C" int vocr_bn_finalize_f32(const double* stats, long long count, const float* gamma, const float* beta,
                                     float* running_mean, float* running_var, float momentum, float eps,
                                     int training, float* scale, float* shift, float* save_mean, float* save_invstd,
-                                    int C, float* aux, vocr_stream_t stream_) {
+                                    int C, float* aux, const float* zmax, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VOCR_REQUIRE(C > 0 && gamma && beta && scale && shift);
   VOCR_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var));
@@ -271,7 +273,7 @@ extern "C" int vocr_bn_finalize_f32(const double* stats, long long count, const 
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, (double)count, gamma, beta, running_mean,
                                                            running_var, momentum, eps, training, scale, shift,
                                                            save_mean, save_invstd, C,
-                                                           reinterpret_cast<unsigned*>(aux));
+                                                           reinterpret_cast<unsigned*>(aux), zmax);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }

@@ -50,6 +50,7 @@ struct LstmArgs {
   float* cst;           // [T,B,2,H]  cell state        (fwd: written if non-null; bwd: read)
   float* xchg;          // fwd: [n_inst][2][16][Hp hi | Hp lo | pad] fp16 | bwd: [n_inst][2][NSL cons][NSL prod][16][US]
   unsigned* flags;      // [n_inst] arrival counters, zeroed before launch
+  float* absmax;        // bwd: receives max |dgates| (bit pattern, atomicMax on the non-negative float), may be null
   int T, B, H, Hp, US, NSL, Tmax, NBT, gpd, n_groups;  // gpd = instance pairs per direction
 };
 
@@ -503,6 +504,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
       int b0[kLstmNI], plen[kLstmNI], tmx[kLstmNI];
       float* px[kLstmNI];
       float dc_reg[kLstmNI], dh_reg[kLstmNI];
+      float da_max = 0.f;  // largest gate-gradient magnitude this thread wrote (operand bound of the GEMMs that follow)
       bool pok[kLstmNI];
       unsigned round[kLstmNI];
 #pragma unroll
@@ -585,6 +587,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
             dg[(size_t)H] = da[1];
             dg[(size_t)2 * H] = da[2];
             dg[(size_t)3 * H] = da[3];
+            da_max = fmaxf(da_max, fmaxf(fmaxf(fabsf(da[0]), fabsf(da[1])), fmaxf(fabsf(da[2]), fabsf(da[3]))));
             dh_reg[i] = 0.f;  // consumed; the next reduce-scatter refills it
           }
           if (k == 0) continue;
@@ -708,6 +711,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) bilstm_bwd_kernel(LstmArgs a)
           PF_ADD(pf_prod, c5, c6);
         }
       }
+      if (a.absmax) {  // non-negative floats order like their bit patterns; NaN (0x7fc00000) wins, so it is not hidden
+        da_max = warp_max(da_max);
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(a.absmax), __float_as_uint(da_max));
+      }
 #ifdef VOCR_LSTM_PROF
       if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 255))
         printf("lstm bwd prof tid %d: total %lld  wait %lld  reduce %lld  grad %lld  sync+frag %lld  prod+store %lld (store %lld) (cycles), Tmax %d\n",
@@ -823,10 +830,11 @@ extern "C" int vocr_bilstm_fwd_f32(const float* xproj, const float* whh, const i
 
 // dout [T,B,2H], gates/cst from the forward pass -> dgates [T,B,2,4H] (gradient w.r.t. xproj; zero beyond lens).
 extern "C" int vocr_bilstm_bwd_f32(const float* dout, const float* whh, const int32_t* lens, const float* gates,
-                                   const float* cst, float* dgates, int T, int B, int H, int Tmax, void* workspace,
-                                   size_t workspace_bytes, vocr_stream_t stream_) {
+                                   const float* cst, float* dgates, float* dgates_absmax, int T, int B, int H, int Tmax,
+                                   void* workspace, size_t workspace_bytes, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VOCR_REQUIRE(T >= 0 && B >= 0 && H >= 1 && Tmax >= 0 && Tmax <= T);
+  if (dgates_absmax && cudaMemsetAsync(dgates_absmax, 0, sizeof(float), stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
   if (T == 0 || B == 0) return VOCR_OK;
   VOCR_REQUIRE(dout && whh && lens && gates && cst && dgates && workspace);
   if (cudaMemsetAsync(dgates, 0, sizeof(float) * (size_t)T * B * 8 * H, stream) != cudaSuccess)
@@ -835,6 +843,7 @@ extern "C" int vocr_bilstm_bwd_f32(const float* dout, const float* whh, const in
   LstmArgs a{};
   a.xproj = dout; a.whh = whh; a.lens = lens; a.out = dgates;
   a.gates = const_cast<float*>(gates); a.cst = const_cast<float*>(cst);
+  a.absmax = dgates_absmax;
   a.T = T; a.B = B; a.H = H; a.Tmax = Tmax;
   return lstm_launch(true, a, workspace, workspace_bytes, stream);
 }

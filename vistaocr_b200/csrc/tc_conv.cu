@@ -39,6 +39,7 @@ struct TcConvParams {
   const int* exp_x;  // FP16 pair operands: device exponents of the activation / weight planes
   const int* exp_w;
   int single;        // 1 = hi planes only, one product per k-step (vocr_set_tc_products(1))
+  unsigned* zmax;    // optional: max |z| over the whole output (atomicMax on the bit pattern of the non-negative float)
 };
 
 template <bool F16>
@@ -139,6 +140,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     float* zrow = p.z + (((size_t)b * p.H + y) * p.W + x) * p.Cout;
     const int n_hi = min(kCvHiAcc, num_kb);
     const int out_shift = F16 ? -(__ldg(p.exp_x) + __ldg(p.exp_w)) : 0;
+    float vmax = 0.f;
     for (int cb = 0; cb < p.BN; cb += 32) {
       float acc[32];
 #pragma unroll
@@ -165,10 +167,15 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
               const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
               v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
             }
+            vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             *reinterpret_cast<float4*>(zrow + n) = v;
           }
         }
       }
+    }
+    if (p.zmax) {
+      vmax = warp_max(vmax);
+      if (lane == 0) atomicMax(p.zmax, __float_as_uint(vmax));
     }
   }
   tc_fence_before();
@@ -289,6 +296,7 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
     const int r = lane_grp * 32 + lane;            // row of the tile = pixel iy*BW + ix
     const int iy = r / p.BW, ix = r - iy * p.BW;
     const int out_shift = F16 ? -(__ldg(p.exp_x) + __ldg(p.exp_w)) : 0;
+    float vmax = 0.f;
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int set = j & 1;
@@ -326,6 +334,7 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
                 v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
               }
+              vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
               *reinterpret_cast<float4*>(zrow + n) = make_float4(v[0], v[1], v[2], v[3]);
             }
           }
@@ -333,6 +342,10 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[set]);
+    }
+    if (p.zmax) {
+      vmax = warp_max(vmax);
+      if (lane == 0) atomicMax(p.zmax, __float_as_uint(vmax));
     }
   }
   tc_fence_before();
@@ -620,7 +633,7 @@ static void pick_tile(int H, int W, int* BW, int* BH) {
 template <bool F16>
 static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp_x, const void* w_hi, const void* w_lo,
                               const int* exp_w, const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
-                              int products, cudaStream_t stream) {
+                              int products, float* zmax, cudaStream_t stream) {
   constexpr int CK = TcElem<F16>::kBK;
   VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % CK == 0 && Cout % 4 == 0);
   VOCR_REQUIRE(products == 0 || products == 1 || products == 3);
@@ -631,6 +644,7 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
   TcConvParams p;
   p.z = z; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.exp_x = exp_x; p.exp_w = exp_w;
+  p.zmax = reinterpret_cast<unsigned*>(zmax);
   p.single = (F16 && resolve_tc_products(products) == 1) ? 1 : 0;
   pick_tile(H, W, &p.BW, &p.BH);
   p.tiles_x = ceil_div(W, p.BW);
@@ -678,14 +692,14 @@ static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp
 extern "C" int vocr_tc_conv3x3_fwd(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                                    const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
                                    vocr_stream_t stream_) {
-  return tc_conv_fwd_launch<false>(x_hi, x_lo, nullptr, w_hi, w_lo, nullptr, bias, z, B, H, W, Cin, Cout, 3,
+  return tc_conv_fwd_launch<false>(x_hi, x_lo, nullptr, w_hi, w_lo, nullptr, bias, z, B, H, W, Cin, Cout, 3, nullptr,
                                    static_cast<cudaStream_t>(stream_));
 }
 extern "C" int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x,
                                        const uint16_t* w_hi, const uint16_t* w_lo, const int32_t* exp_w,
                                        const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
-                                       int products, vocr_stream_t stream_) {
-  return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, z, B, H, W, Cin, Cout, products,
+                                       int products, float* zmax, vocr_stream_t stream_) {
+  return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, z, B, H, W, Cin, Cout, products, zmax,
                                   static_cast<cudaStream_t>(stream_));
 }
 

@@ -171,13 +171,13 @@ class _Linear(torch.autograd.Function):
     """y = x W^T + b (optionally ReLU); x [M,K], W [N,K] (nn.Linear layout)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, relu):
+    def forward(ctx, x, w, b, relu, x_bound=None):
         x, w = _c(x), _c(w)
         _lib.require_cuda(x, "x", F32)
         M, K = x.shape
         N = w.shape[0]
         y = torch.empty((M, N), dtype=F32, device=x.device)
-        xo, wo = Operand(x), Operand(w)
+        xo, wo = Operand(x, bound=x_bound), Operand(w)
         mm(0, 1, M, N, K, xo, K, wo, K, y, N, bias=b, relu=relu)
         ctx.ops = (xo, wo)
         ctx.relu = relu
@@ -206,11 +206,12 @@ class _Linear(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((N,), dtype=F32, device=x.device)
             colsum(dy, M, N, N, db)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def linear(x, w, b=None, relu=False):
-    return _Linear.apply(x, w, b, relu)
+def linear(x, w, b=None, relu=False, x_bound=None):
+    """x_bound: optional device scalar >= max|x| (spares the operand split its abs-max pass)."""
+    return _Linear.apply(x, w, b, relu, x_bound)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -261,11 +262,12 @@ def _tc_conv_wgrad(x_s, dz_s, B, H, W, Cin, Cout):
     return dw
 
 
-def _tc_conv_fwd16(x_s, w_s, bias, B, H, W, Cin, Cout):
-    """x_s, w_s: (hi, lo, state) FP16 pair planes; x NHWC [B,H,W,Cin], w K-major [Cout, 9*Cin]."""
+def _tc_conv_fwd16(x_s, w_s, bias, B, H, W, Cin, Cout, zmax=None):
+    """x_s, w_s: (hi, lo, state) FP16 pair planes; x NHWC [B,H,W,Cin], w K-major [Cout, 9*Cin].  zmax: optional zeroed
+    device scalar that receives max |z| from the epilogue."""
     z = torch.empty((B, H, W, Cout), dtype=F32, device=x_s[0].device)
     st = lib().vocr_tc_conv3x3_fwd_f16(ptr(x_s[0]), ptr(x_s[1]), ptr(x_s[2]), ptr(w_s[0]), ptr(w_s[1]), ptr(w_s[2]),
-                                       ptr(bias), ptr(z), B, H, W, Cin, Cout, _PRODUCTS[0], stream())
+                                       ptr(bias), ptr(z), B, H, W, Cin, Cout, _PRODUCTS[0], ptr(zmax), stream())
     check(st, "vocr_tc_conv3x3_fwd_f16")
     return z
 
@@ -298,8 +300,10 @@ def _narrow(Cin, Cout):
     return USE_F16 and Cin < 64 and Cin % 8 == 0 and Cout % 8 == 0
 
 
-def conv3x3(x, weight, bias, x_op=None):
-    """z = conv3x3_pad1(x) + bias, NHWC; picks the tensor-core kernel when Cin % 32 == 0.  Returns (z, x_operand)."""
+def conv3x3(x, weight, bias, x_op=None, zmax=None):
+    """z = conv3x3_pad1(x) + bias, NHWC; picks the tensor-core kernel when Cin % 32 == 0.  Returns (z, x_operand).
+    zmax (optional zeroed device scalar) receives max |z| when the FP16-pair implicit-GEMM kernel runs (it stays 0 on the
+    other paths: callers must treat 0 as "not measured")."""
     B, H, W, Cin = x.shape
     Cout = weight.shape[0]
     if _narrow(Cin, Cout):
@@ -313,7 +317,9 @@ def conv3x3(x, weight, bias, x_op=None):
     if USE_F16 and Cin % 64 == 0 and Cout % 4 == 0:
         x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x, bound=getattr(x, "_vocr_bound", None))
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
-        return _tc_conv_fwd16(x_op.split16(), wn.split16(), bias, B, H, W, Cin, Cout), x_op
+        if zmax is not None:
+            zmax.measured = True
+        return _tc_conv_fwd16(x_op.split16(), wn.split16(), bias, B, H, W, Cin, Cout, zmax), x_op
     if USE_TC and Cin % 32 == 0 and Cout % 4 == 0:
         x_op = x_op or getattr(x, "_vocr_op", None) or Operand(x)
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
@@ -378,7 +384,12 @@ class _ConvBNReLU(torch.autograd.Function):
         Cout = weight.shape[0]
         dev = x.device
         stats = torch.zeros((2 * Cout,), dtype=torch.float64, device=dev) if training else None
-        z, x_op = conv3x3(x, weight, bias)
+        # eval mode: the convolution's epilogue measures max |z|, from which bn_finalize bounds the activations - the
+        # apply kernel can then emit the next layer's FP16 pair planes directly (no abs-max + split passes)
+        zmax = torch.zeros((1,), dtype=F32, device=dev) if (USE_F16 and not training) else None
+        z, x_op = conv3x3(x, weight, bias, zmax=zmax)
+        if zmax is not None and not getattr(zmax, "measured", False):
+            zmax = None
         if training:
             colstats(z, Cout, stats)
         ctx.x_op = x_op
@@ -389,7 +400,7 @@ class _ConvBNReLU(torch.autograd.Function):
         aux = torch.empty((2,), dtype=F32, device=dev)  # [0] activation bound, [1] max|scale| (FP16 pair planes)
         st = lib().vocr_bn_finalize_f32(ptr(stats), B * H * W, ptr(gamma), ptr(beta), ptr(running_mean),
                                         ptr(running_var), float(momentum), float(eps), int(training), ptr(scale),
-                                        ptr(shift), ptr(mean), ptr(invstd), Cout, ptr(aux), stream())
+                                        ptr(shift), ptr(mean), ptr(invstd), Cout, ptr(aux), ptr(zmax), stream())
         check(st, "vocr_bn_finalize_f32")
         if seq_layout:
             a = torch.empty((W, B, H * Cout), dtype=F32, device=dev)
@@ -402,7 +413,8 @@ class _ConvBNReLU(torch.autograd.Function):
         a_hi = torch.empty_like(a) if want_split else None
         a_lo = torch.empty_like(a) if want_split else None
         # ... or as FP16 pair planes (the analytic bound of bn_finalize needs batch statistics)
-        want16 = USE_F16 and training and not seq_layout and Cout % 64 == 0 and planes
+        bounded = training or zmax is not None  # aux[0] holds a valid bound of the activations
+        want16 = USE_F16 and bounded and not seq_layout and Cout % 64 == 0 and planes
         a_hi16 = torch.empty(a.shape, dtype=torch.float16, device=dev) if want16 else None
         a_lo16 = torch.empty(a.shape, dtype=torch.float16, device=dev) if want16 else None
         pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
@@ -415,7 +427,7 @@ class _ConvBNReLU(torch.autograd.Function):
             # activation and both planes alive until Python's cyclic GC runs - several GB per step
             a._vocr_op = Operand(None, (a_hi, a_lo) if want_split else None,
                                  (a_hi16, a_lo16, pstate) if want16 else None)
-        if USE_F16 and training and not seq_layout:
+        if USE_F16 and bounded:
             a._vocr_bound = aux  # aux[0] bounds a (and anything pooled from it): lets a later split skip its absmax
         ctx.save_for_backward(x, weight, z, scale, shift, mean, invstd, aux)
         ctx.dims = (B, H, W, Cin, Cout, strides, bool(training))
@@ -594,14 +606,15 @@ class _BiLSTMLayer(torch.autograd.Function):
         dgates = torch.empty((T, B, 2, 4 * H), dtype=F32, device=dev)
         wsb = lib().vocr_bilstm_workspace_size(ctx.tmax, B, H, 1)
         ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
-        st = lib().vocr_bilstm_bwd_f32(ptr(dout), ptr(w_hh), ptr(lens_dev), ptr(gates), ptr(cst), ptr(dgates), T, B,
-                                       H, ctx.tmax, ptr(ws), wsb, stream())
+        dg_max = torch.empty((1,), dtype=F32, device=dev)  # max |dgates| from the kernel: no abs-max pass for the GEMMs
+        st = lib().vocr_bilstm_bwd_f32(ptr(dout), ptr(w_hh), ptr(lens_dev), ptr(gates), ptr(cst), ptr(dgates), ptr(dg_max),
+                                       T, B, H, ctx.tmax, ptr(ws), wsb, stream())
         check(st, "vocr_bilstm_bwd_f32")
         dx = dw_ih = dw_hh = db = None
         M = T * B
         xo, wo = ctx.ops
         ctx.ops = None
-        dgo, outo = Operand(dgates), Operand(out, bound=const_scalar(dev, 1.0))  # |h| < 1
+        dgo, outo = Operand(dgates, bound=dg_max), Operand(out, bound=const_scalar(dev, 1.0))  # |h| < 1
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             mm(0, 0, M, Din, 8 * H, dgo, 8 * H, wo, Din, dx, Din)
