@@ -774,7 +774,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="train_cfg2",
                     choices=["train_cfg2", "train_cfg3", "decode_cfg5", "decode_cfg1", "ctc_cfg4"])
-    ap.add_argument("--batch", type=int, default=256, help="decode_cfg5: lines per batch")
+    ap.add_argument("--batch", type=int, default=448,
+                    help="decode_cfg5: lines per batch (a multiple of 224 = 7 clusters x 32 samples: the BiLSTM forward "
+                         "kernel keeps 7 clusters of 16 CTAs resident, so 448 lines are exactly four rounds per direction)")
     ap.add_argument("--eager", action="store_true", help="time the eager launch path instead of CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="skip the side metrics and the in-line CPU baseline")
     args = ap.parse_args()
