@@ -168,7 +168,9 @@ def test_fracpool_bit_exact(cuda, B, H, W, C):
 
 @pytest.mark.parametrize("T,B,D,H,ragged", [(9, 3, 5, 8, True), (20, 5, 16, 24, True), (7, 33, 12, 16, True),
                                             (12, 2, 8, 40, False), (6, 70, 4, 8, True), (5, 4, 128, 512, True),
-                                            (12, 20, 16, 256, True), (8, 18, 8, 500, True), (6, 5, 8, 200, True)])
+                                            (12, 20, 16, 256, True), (8, 18, 8, 500, True), (6, 5, 8, 200, True),
+                                            # batches >= 128 use 64-sample cluster work items (W_lo split TMEM / smem)
+                                            (7, 130, 12, 512, True), (6, 200, 8, 72, True), (5, 448, 4, 264, True)])
 def test_bilstm_layer(cuda, T, B, D, H, ragged):
     from vistaocr_b200 import ops
     g = torch.Generator().manual_seed(T * 100 + B)

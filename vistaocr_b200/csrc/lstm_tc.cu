@@ -34,17 +34,30 @@
 namespace vocr {
 
 constexpr int kClM = 128;             // gate rows per CTA = UMMA M (32 unit slots x 4 gates)
-constexpr int kClN = 32;              // samples per cluster work item = UMMA N
 constexpr int kClSize = 16;           // CTAs per cluster
 constexpr int kClMaxKB = 8;           // k-blocks of 64 units (H <= 512)
 constexpr int kClThreads = 320;       // 8 epilogue warps, 1 MMA warp, 1 input-projection loader warp
 constexpr uint32_t kClWloKb = kClM * 128;                  // W_lo bytes per k-block: 16 KB
-constexpr uint32_t kClChunk = 2 * (kClN / 8) * 128;        // h tile bytes per k-chunk of 8 units (2 planes): 1 KB
-constexpr uint32_t kClTileBytes = 64 * kClChunk;           // h tile: 64 k-chunks = 64 KB
-constexpr int kClXsLd = 136;                               // row stride (floats) of the staged input projections
-constexpr uint32_t kClXsBytes = kClN * kClXsLd * 4;        // 17 KB
-constexpr uint32_t kColA = 0, kColD = 256;                 // TMEM columns: W_hi operand | accumulators
+constexpr uint32_t kColA = 0, kColAlo = 256;               // TMEM columns: W_hi operand | (NS = 64) first half of W_lo
 constexpr float kClLoScale = 2048.f;
+
+// Geometry of one cluster work item = (direction, NS samples).  NS = 32: four items of a 64-line batch run on four clusters
+// in parallel (training).  NS = 64 (batches >= 128): every product instruction streams the same 4 KB of W whatever its N,
+// so twice the samples per instruction halve the per-sample cost; the 128-KB operand tile then only fits because the
+// first half of W_lo moves into TMEM next to W_hi (TS-mode products for k < 256, SS-mode above).
+template <int NS>
+struct ClGeom {
+  static constexpr uint32_t kPlane = (NS / 8) * 128;          // one plane of a k-chunk of 8 units: NS rows x 16 B
+  static constexpr uint32_t kChunk = 2 * kPlane;              // hi plane | lo plane
+  static constexpr uint32_t kTileBytes = 64 * kChunk;         // operand tile of h: 64 / 128 KB
+  static constexpr int kWloSmemKB = (NS == 32) ? 8 : 4;       // k-blocks of W_lo kept in shared memory (the upper ones)
+  static constexpr int kWloTmemKB = kClMaxKB - kWloSmemKB;    // ... and in TMEM (the lower ones)
+  static constexpr int kXsLd = (NS == 32) ? 136 : 132;        // row stride (floats) of the staged input projections
+  static constexpr uint32_t kXsBytes = NS * kXsLd * 4;
+  static constexpr uint32_t kColD = (NS == 32) ? 256 : 384;   // accumulator: 2 NS columns (hi.hi | cross terms)
+  static constexpr uint32_t kStageBytes = 4 * kChunk;         // a CTA's piece: up to 4 k-chunks
+  static constexpr size_t kSmem = (size_t)kWloSmemKB * kClWloKb + kTileBytes + kXsBytes + 64 + 1024;
+};
 
 struct LstmClArgs {
   const float* xproj;   // [T,B,2,4H]
@@ -53,7 +66,7 @@ struct LstmClArgs {
   float* out;           // [T,B,2H]  (pre-zeroed)
   float* gates;         // [T,B,2,4H] activated i,f,g,o (may be null)
   float* cst;           // [T,B,2,H]  (may be null)
-  unsigned char* stage; // [clusters][16 CTAs][2 parities][4 KB] staging of the published pieces
+  unsigned char* stage; // [clusters][16 CTAs][2 parities][piece] staging of the published pieces
   int T, B, H, KB, US, NSL, Tmax, NG, n_items;
 };
 
@@ -122,15 +135,18 @@ __device__ __forceinline__ void cl_cluster_sync() {
 // the 256 epilogue threads only
 __device__ __forceinline__ void cl_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+template <int NS>
 __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmClArgs a) {
+  using G = ClGeom<NS>;
+  constexpr int NP = NS / 32;  // epilogue passes: a warp handles 16 samples per pass
   extern __shared__ unsigned char cl_smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cl_smem_raw) + 1023) & ~uintptr_t(1023));
   const int KB = a.KB, H = a.H, US = a.US;
-  unsigned char* Wlo = smem;                                      // [KB][128 rows x 128 B] SW128 K-major
-  unsigned char* Ht = Wlo + (size_t)kClMaxKB * kClWloKb;          // [64 k-chunks][hi 512 B | lo 512 B] SWIZZLE_NONE
-  float* xs = reinterpret_cast<float*>(Ht + kClTileBytes);        // [32 samples][136]: gate g, unit u at g*32 + u
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + kClXsBytes);
+  unsigned char* Wlo = smem;                                         // [kWloSmemKB][128 rows x 128 B] SW128 K-major
+  unsigned char* Ht = Wlo + (size_t)G::kWloSmemKB * kClWloKb;        // [64 k-chunks][hi plane | lo plane] SWIZZLE_NONE
+  float* xs = reinterpret_cast<float*>(Ht + G::kTileBytes);          // [NS samples][kXsLd]: gate g, unit u at g*32 + u
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xs) + G::kXsBytes);
   uint64_t* full = bars;           // h tile of the step landed (1 arrival + NSL pieces of tx bytes)
   uint64_t* mma_done = bars + 1;   // this CTA's products of the step retired (tcgen05.commit)
   uint64_t* tile_free = bars + 2;  // EVERY CTA's products of the step retired (NSL multicast commits)
@@ -144,7 +160,7 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
   const int nu = max(0, min(US, H - u0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint16_t cta_mask = (uint16_t)((1u << a.NSL) - 1u);
-  const uint32_t piece_bytes = (uint32_t)(US / 8) * kClChunk;
+  const uint32_t piece_bytes = (uint32_t)(US / 8) * G::kChunk;
   const bool active_cta = slice < a.NSL;
 
   if (tid == 0) {
@@ -157,7 +173,7 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
   }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
   // the operand tile starts as zeros: unit columns nobody publishes (H < 64 KB) and the state of step 0
-  for (int i = tid; i < (int)(kClTileBytes / 16); i += kClThreads) reinterpret_cast<uint4*>(Ht)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(G::kTileBytes / 16); i += kClThreads) reinterpret_cast<uint4*>(Ht)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -173,41 +189,49 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
 
   unsigned n_full = 0, n_done = 0, n_free = 0, n_xsfull = 0, n_xsfree = 0;
   int loaded_dir = -1;
-  unsigned char* stage = a.stage + ((size_t)(cluster_id * kClSize + slice) * 2) * 4096;
+  unsigned char* stage = a.stage + ((size_t)(cluster_id * kClSize + slice) * 2) * G::kStageBytes;
 
   for (int item = cluster_id; item < a.n_items; item += n_clusters) {
     const int dir = item & 1, grp = item >> 1;
-    const int b_base = grp * kClN;
+    const int b_base = grp * NS;
     int tm = 0;  // steps of this item: its longest sample
-    for (int j = b_base; j < min(a.B, b_base + kClN); ++j) tm = max(tm, min(a.lens[j], a.Tmax));
+    for (int j = b_base; j < min(a.B, b_base + NS); ++j) tm = max(tm, min(a.lens[j], a.Tmax));
 
     if (loaded_dir != dir) {
       // ---- W slice: row m = 32q + 4 u8 + g  <->  gate g of unit slot U = 8q + u8 ------------------------------------
       const float* wd = a.whh + (size_t)dir * 4 * H * H;
-      if (warp < 4) {  // hi plane -> TMEM, lane m, column k/2 (two halves per column)
-        const int m = 32 * warp + lane, g = lane & 3, U = 8 * warp + (lane >> 2);
+      if (warp < 4) {  // TMEM planes: lane m, column k/2 (two halves per column): W_hi, and W_lo for the lower k-blocks
+        const int g = lane & 3, U = 8 * warp + (lane >> 2);
         const float* wr = wd + ((size_t)g * H + u0 + U) * H;
-        for (int c0 = 0; c0 < KB * 32; c0 += 32) {
-          uint32_t v[32];
+        for (int plane = 0; plane < (G::kWloTmemKB > 0 ? 2 : 1); ++plane) {
+          const int ncols = (plane == 0 ? KB : min(KB, G::kWloTmemKB)) * 32;
+          for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int k = 2 * (c0 + c);
-            const float w0 = (U < nu && k < H) ? __ldg(wr + k) : 0.f, w1 = (U < nu && k + 1 < H) ? __ldg(wr + k + 1) : 0.f;
-            v[c] = (uint32_t)__half_as_ushort(__float2half_rn(w0)) | ((uint32_t)__half_as_ushort(__float2half_rn(w1)) << 16);
+            for (int c = 0; c < 32; ++c) {
+              const int k = 2 * (c0 + c);
+              const float w0 = (U < nu && k < H) ? __ldg(wr + k) : 0.f, w1 = (U < nu && k + 1 < H) ? __ldg(wr + k + 1) : 0.f;
+              __half h0, l0, h1, l1;
+              cl_split_f16(w0, h0, l0);
+              cl_split_f16(w1, h1, l1);
+              v[c] = plane == 0 ? ((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16))
+                                : ((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16));
+            }
+            cl_tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + (plane == 0 ? kColA : kColAlo) + c0, v);
           }
-          cl_tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + kColA + c0, v);
-          (void)m;
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      for (int i = tid; i < kClM * KB * 64; i += kClThreads) {  // lo plane -> shared memory
-        const int m = i / (KB * 64), k = i - m * (KB * 64);
+      const int k_lo0 = G::kWloTmemKB * 64;  // first k of W_lo that lives in shared memory
+      for (int i = tid; i < kClM * (KB * 64 - min(KB * 64, k_lo0)); i += kClThreads) {
+        const int kw = KB * 64 - k_lo0;
+        const int m = i / kw, k = k_lo0 + (i - m * kw);
         const int q = m >> 5, g = m & 3, U = 8 * q + ((m & 31) >> 2);
         float v = 0.f;
         if (U < nu && k < H) v = __ldg(wd + ((size_t)g * H + u0 + U) * H + k);
         __half hi, lo;
         cl_split_f16(v, hi, lo);
-        *reinterpret_cast<__half*>(Wlo + (size_t)(k >> 6) * kClWloKb + cl_sw128(m, k & 63)) = lo;
+        *reinterpret_cast<__half*>(Wlo + (size_t)((k >> 6) - G::kWloTmemKB) * kClWloKb + cl_sw128(m, k & 63)) = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       loaded_dir = dir;
@@ -218,188 +242,160 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
 
     if (warp < 8) {
       // ===================================== epilogue warps ======================================================
-      const int q = warp & 3, hh = warp >> 2;       // TMEM quadrant, half of the 32 samples
+      const int q = warp & 3, hh = warp >> 2;       // TMEM quadrant, half of a 32-sample pass
       const int u8 = lane >> 2, g = lane & 3;
       const int U = 8 * q + u8;                     // unit slot of this thread
       const bool unit_ok = U < nu;
-      int bs[4], len[4];
-      float c_reg[4], h_reg[4];
+      int bs[NP][4], len[NP][4];
+      float c_reg[NP][4], h_reg[NP][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = 16 * hh + 4 * j + g;          // this thread's four samples
-        bs[j] = b_base + n;
-        len[j] = (bs[j] < a.B) ? min(a.lens[bs[j]], a.Tmax) : 0;
-        c_reg[j] = h_reg[j] = 0.f;
-      }
-#ifdef VOCR_LSTM_PROF
-      long long pf_wait = 0, pf_ld = 0, pf_gate = 0, pf_pub = 0, pf_out = 0, pf_free = 0, pf_fence = 0, pf_tld = 0, pf_xs = 0, pf_t0 = clock64();
-#endif
+      for (int ps = 0; ps < NP; ++ps)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = 32 * ps + 16 * hh + 4 * j + g;  // this thread's samples
+          bs[ps][j] = b_base + n;
+          len[ps][j] = (bs[ps][j] < a.B) ? min(a.lens[bs[ps][j]], a.Tmax) : 0;
+          c_reg[ps][j] = h_reg[ps][j] = 0.f;
+        }
       for (int k = 0; k < tm; ++k) {
-#ifdef VOCR_LSTM_PROF
-        const long long c0 = clock64();
-#endif
-        float pre[4][4];  // [gate][j]
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pre[gg][j] = 0.f;
         if (k > 0) {
           mbar_wait_or_trap(mma_done, n_done & 1u);
           ++n_done;
           tc_fence_after();
-#ifdef VOCR_LSTM_PROF
-          pf_wait += clock64() - c0;
-#endif
-          // D = W_hi . [h_hi | h_lo] (columns 0-31 | 32-63); W_lo . h_hi is accumulated into columns 32-63 as well (both
-          // cross terms carry the 2^-11 scale)
-          const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + kColD + 16 * hh;
-          uint32_t a_hh[16], a_x[16];
-          float v[16];
-          cl_tmem_ld16(tbase, a_hh);
-          cl_tmem_ld16(tbase + kClN, a_x);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = fmaf(__uint_as_float(a_x[c]), 1.f / kClLoScale, __uint_as_float(a_hh[c]));
-          tc_fence_before();
-#ifdef VOCR_LSTM_PROF
-          pf_tld += clock64() - c0;
-#endif
-          // regroup: this lane holds gate g of unit U for 16 samples.  A 4 x 4 transpose over the four sibling lanes (same
-          // u8; two xor-shuffle rounds, static register indices only) leaves it with all four gates of the samples
-          // c = 4j + g.
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x0 = v[4 * j], x1 = v[4 * j + 1], x2 = v[4 * j + 2], x3 = v[4 * j + 3];
-            const bool o1 = (g & 1) != 0, o2 = (g & 2) != 0;
-            float s0 = o1 ? x0 : x1, s1 = o1 ? x2 : x3;
-            s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
-            s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-            if (o1) { x0 = s0; x2 = s1; } else { x1 = s0; x3 = s1; }
-            s0 = o2 ? x0 : x2;
-            s1 = o2 ? x1 : x3;
-            s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
-            s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
-            if (o2) { x0 = s0; x1 = s1; } else { x2 = s0; x3 = s1; }
-            pre[0][j] = x0; pre[1][j] = x1; pre[2][j] = x2; pre[3][j] = x3;
-          }
         }
-#ifdef VOCR_LSTM_PROF
-        const long long c1 = clock64();
-#endif
-        // input projections staged by the loader warp
-        mbar_wait_or_trap(xs_full, n_xsfull & 1u);
-        ++n_xsfull;
-#ifdef VOCR_LSTM_PROF
-        pf_xs += clock64() - c1;
-#endif
-        bool act[4];
+        unsigned char* pc = stage + (size_t)(k & 1) * G::kStageBytes;
+        float ig[NP][4], fg[NP][4], gv[NP][4], og[NP][4];
+        bool act[NP][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          act[j] = unit_ok && k < len[j];
-          if (act[j]) {
-            const float* xr = xs + (16 * hh + 4 * j + g) * kClXsLd + U;
+        for (int ps = 0; ps < NP; ++ps) {
+          const int sb = 32 * ps + 16 * hh;  // first of the 16 samples (accumulator columns) of this pass
+          float pre[4][4];                   // [gate][j]
 #pragma unroll
-            for (int gg = 0; gg < 4; ++gg) pre[gg][j] += xr[gg * 32];
-          }
-        }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xs_free)) : "memory");
-        float ig[4], fg[4], gv[4], og[4];
+          for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ig[j] = fg[j] = gv[j] = og[j] = 0.f;
-          if (act[j]) {
-            ig[j] = cl_sigmoidf(pre[0][j]); fg[j] = cl_sigmoidf(pre[1][j]);
-            gv[j] = cl_tanhf(pre[2][j]);    og[j] = cl_sigmoidf(pre[3][j]);
-            c_reg[j] = fmaf(fg[j], c_reg[j], ig[j] * gv[j]);
-            h_reg[j] = og[j] * cl_tanhf(c_reg[j]);
-          }
-        }
-#ifdef VOCR_LSTM_PROF
-        const long long c2 = clock64();
-#endif
-        if (k + 1 < tm) {
-          // publish h_k: this CTA's piece of the operand tile, laid out exactly like the tile (k-chunk q of the piece,
-          // plane, row group n/8, row n%8, unit u8): finished / padding samples and missing units publish their state
-          // (zeros), the consumers take the whole piece
-          unsigned char* pc = stage + (size_t)(k & 1) * 4096;
-          if (U < US) {
+            for (int j = 0; j < 4; ++j) pre[gg][j] = 0.f;
+          if (k > 0) {
+            // D = W_hi . [h_hi | h_lo] (columns 0..NS-1 | NS..2NS-1); W_lo . h_hi is accumulated into the second half as
+            // well (both cross terms carry the 2^-11 scale)
+            const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + G::kColD + sb;
+            uint32_t a_hh[16], a_x[16];
+            float v[16];
+            cl_tmem_ld16(tbase, a_hh);
+            cl_tmem_ld16(tbase + NS, a_x);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = fmaf(__uint_as_float(a_x[c]), 1.f / kClLoScale, __uint_as_float(a_hh[c]));
+            // regroup: this lane holds gate g of unit U for 16 samples.  A 4 x 4 transpose over the four sibling lanes
+            // (same u8; two xor-shuffle rounds, static register indices only) leaves it with all four gates of the
+            // samples c = 4j + g.
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int n = 16 * hh + 4 * j + g;
-              __half hi, lo;
-              cl_split_f16(h_reg[j], hi, lo);
-              unsigned char* p = pc + (size_t)q * kClChunk + (n >> 3) * 128 + (n & 7) * 16 + u8 * 2;
-              *reinterpret_cast<__half*>(p) = hi;
-              *reinterpret_cast<__half*>(p + 512) = lo;
+              float x0 = v[4 * j], x1 = v[4 * j + 1], x2 = v[4 * j + 2], x3 = v[4 * j + 3];
+              const bool o1 = (g & 1) != 0, o2 = (g & 2) != 0;
+              float s0 = o1 ? x0 : x1, s1 = o1 ? x2 : x3;
+              s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+              s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+              if (o1) { x0 = s0; x2 = s1; } else { x1 = s0; x3 = s1; }
+              s0 = o2 ? x0 : x2;
+              s1 = o2 ? x1 : x3;
+              s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+              s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+              if (o2) { x0 = s0; x1 = s1; } else { x2 = s0; x3 = s1; }
+              pre[0][j] = x0; pre[1][j] = x1; pre[2][j] = x2; pre[3][j] = x3;
             }
           }
+          if (ps == 0) {  // input projections staged by the loader warp
+            if (k > 0) tc_fence_before();
+            mbar_wait_or_trap(xs_full, n_xsfull & 1u);
+            ++n_xsfull;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            act[ps][j] = unit_ok && k < len[ps][j];
+            if (act[ps][j]) {
+              const float* xr = xs + (sb + 4 * j + g) * G::kXsLd + U;
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) pre[gg][j] += xr[gg * 32];
+            }
+          }
+          if (ps == NP - 1) {
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xs_free)) : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ig[ps][j] = fg[ps][j] = gv[ps][j] = og[ps][j] = 0.f;
+            if (act[ps][j]) {
+              ig[ps][j] = cl_sigmoidf(pre[0][j]); fg[ps][j] = cl_sigmoidf(pre[1][j]);
+              gv[ps][j] = cl_tanhf(pre[2][j]);    og[ps][j] = cl_sigmoidf(pre[3][j]);
+              c_reg[ps][j] = fmaf(fg[ps][j], c_reg[ps][j], ig[ps][j] * gv[ps][j]);
+              h_reg[ps][j] = og[ps][j] * cl_tanhf(c_reg[ps][j]);
+            }
+          }
+          if (k + 1 < tm && U < US) {
+            // publish h_k: this CTA's piece of the operand tile, laid out exactly like the tile (k-chunk q of the piece,
+            // plane, row group n/8, row n%8, unit u8): finished / padding samples and missing units publish their state
+            // (zeros), the consumers take the whole piece
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = sb + 4 * j + g;
+              __half hi, lo;
+              cl_split_f16(h_reg[ps][j], hi, lo);
+              unsigned char* p = pc + (size_t)q * G::kChunk + (n >> 3) * 128 + (n & 7) * 16 + u8 * 2;
+              *reinterpret_cast<__half*>(p) = hi;
+              *reinterpret_cast<__half*>(p + G::kPlane) = lo;
+            }
+          }
+        }
+        if (k + 1 < tm) {
           cl_epi_sync();
           if (tid == 0) {
-#ifdef VOCR_LSTM_PROF
-            const long long p0 = clock64();
-#endif
             // every CTA's products of step k have retired: the tiles may be overwritten (k = 0: nothing ran yet)
             if (k > 0) {
               mbar_wait_or_trap(tile_free, n_free & 1u);
               ++n_free;
             }
-#ifdef VOCR_LSTM_PROF
-            const long long p1 = clock64();
-#endif
             asm volatile("fence.proxy.async.global;" ::: "memory");
-#ifdef VOCR_LSTM_PROF
-            pf_free += p1 - p0; pf_fence += clock64() - p1;
-#endif
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                 ::"r"(smem_u32(Ht + (size_t)slice * piece_bytes)), "l"(pc), "r"(piece_bytes), "r"(smem_u32(full)), "h"(cta_mask)
                 : "memory");
           }
         }
-#ifdef VOCR_LSTM_PROF
-        const long long c3 = clock64();
-#endif
+        // the layer's outputs (and what backward needs) are written after the exchange has been started: off the chain
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (act[j]) {
-            const int tt = dir == 0 ? k : len[j] - 1 - k;
-            const size_t tb_ = (size_t)tt * a.B + bs[j];
-            a.out[(tb_ * 2 + dir) * H + u0 + U] = h_reg[j];
-            if (a.gates) {
-              float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + U;
-              gp[0] = ig[j];
-              gp[(size_t)H] = fg[j];
-              gp[(size_t)2 * H] = gv[j];
-              gp[(size_t)3 * H] = og[j];
+        for (int ps = 0; ps < NP; ++ps)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (act[ps][j]) {
+              const int tt = dir == 0 ? k : len[ps][j] - 1 - k;
+              const size_t tb_ = (size_t)tt * a.B + bs[ps][j];
+              a.out[(tb_ * 2 + dir) * H + u0 + U] = h_reg[ps][j];
+              if (a.gates) {
+                float* gp = a.gates + (tb_ * 2 + dir) * 4 * H + u0 + U;
+                gp[0] = ig[ps][j];
+                gp[(size_t)H] = fg[ps][j];
+                gp[(size_t)2 * H] = gv[ps][j];
+                gp[(size_t)3 * H] = og[ps][j];
+              }
+              if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + U] = c_reg[ps][j];
             }
-            if (a.cst) a.cst[(tb_ * 2 + dir) * H + u0 + U] = c_reg[j];
-          }
-#ifdef VOCR_LSTM_PROF
-        const long long c4 = clock64();
-        pf_ld += c1 - c0; pf_gate += c2 - c1; pf_pub += c3 - c2; pf_out += c4 - c3;
-#endif
       }
       if (tid == 0 && tm > 1) {  // the last step's multicast commits (keeps the phase counter in step)
         mbar_wait_or_trap(tile_free, n_free & 1u);
         ++n_free;
       }
-#ifdef VOCR_LSTM_PROF
-      if (blockIdx.x == 3 && (tid == 0 || tid == 255))
-        printf("lstm cluster epilogue tid %d: steps %d total %lld  wait-mma %lld  wait+tmem-ld+regroup %lld (through tmem-ld %lld)  xproj+gates %lld (wait xs %lld)  publish %lld (wait tile_free %lld, fence %lld)  out %lld\n",
-               tid, tm, clock64() - pf_t0, pf_wait, pf_ld, pf_tld, pf_gate, pf_xs, pf_pub, pf_free, pf_fence, pf_out);
-#endif
     } else if (warp == 8) {
       // ===================================== MMA issuer ==========================================================
       if (lane == 0) {
-        // instruction descriptors: D = F32, A / B = F16 K-major, M = 128, N = 64 (hi | lo planes of h side by side) or 32
-        const uint32_t idesc64 = (1u << 4) | ((uint32_t)(2 * kClN >> 3) << 17) | ((uint32_t)(kClM >> 4) << 24);
-        const uint32_t idesc32 = (1u << 4) | ((uint32_t)(kClN >> 3) << 17) | ((uint32_t)(kClM >> 4) << 24);
-        // descriptors advance by constants: W_lo 32 B per k-step inside a k-block of 16 KB, h two k-chunks (2 KB) per
-        // k-step; the start-address field counts 16-byte units
+        // instruction descriptors: D = F32, A / B = F16 K-major, M = 128, N = 2 NS (hi | lo planes of h side by side) or NS
+        const uint32_t idesc_w = (1u << 4) | ((uint32_t)(2 * NS >> 3) << 17) | ((uint32_t)(kClM >> 4) << 24);
+        const uint32_t idesc_n = (1u << 4) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(kClM >> 4) << 24);
+        // descriptors advance by constants: W_lo 32 B per k-step inside a k-block of 16 KB, h two k-chunks per k-step; the
+        // start-address field counts 16-byte units
         const uint64_t d_wlo0 = make_desc(smem_u32(Wlo), 16, 1024, 2);
-        const uint64_t d_h0 = make_desc(smem_u32(Ht), kClChunk, 128, 0);
-        const uint32_t t_a = tmem_base + kColA, t_d1 = tmem_base + kColD, t_d2 = tmem_base + kColD + kClN;
+        const uint64_t d_h0 = make_desc(smem_u32(Ht), G::kChunk, 128, 0);
+        const uint32_t t_a = tmem_base + kColA, t_alo = tmem_base + kColAlo, t_d = tmem_base + G::kColD;
 #ifdef VOCR_LSTM_PROF
         long long mf_wait = 0, mf_issue = 0;
 #endif
@@ -407,7 +403,7 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
 #ifdef VOCR_LSTM_PROF
           const long long m0 = clock64();
 #endif
-          mbar_arrive_expect_tx(full, (uint32_t)a.NSL * piece_bytes);  // arm: the 16 pieces of h_{k-1}
+          mbar_arrive_expect_tx(full, (uint32_t)a.NSL * piece_bytes);  // arm: the pieces of h_{k-1}
           mbar_wait_or_trap(full, n_full & 1u);
           ++n_full;
           tc_fence_after();
@@ -419,15 +415,15 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
             if (kb < KB) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t d_h = d_h0 + (uint64_t)(((kb * 8 + ks * 2) * kClChunk) >> 4);
-                const uint64_t d_wlo = d_wlo0 + (uint64_t)((kb * kClWloKb + ks * 32) >> 4);
+                const uint64_t d_h = d_h0 + (uint64_t)(((kb * 8 + ks * 2) * G::kChunk) >> 4);
                 const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-#ifndef VOCR_LSTM_EXP_NO_TS
-                cl_umma_ts(t_d1, t_a + (uint32_t)(kb * 32 + ks * 8), d_h, idesc64, first);  // W_hi . [h_hi | h_lo]
-#endif
-#ifndef VOCR_LSTM_EXP_NO_SS
-                umma_f16(t_d2, d_wlo, d_h, idesc32, 1u);                       // += W_lo . h_hi (the hi.lo columns)
-#endif
+                cl_umma_ts(t_d, t_a + (uint32_t)(kb * 32 + ks * 8), d_h, idesc_w, first);  // W_hi . [h_hi | h_lo]
+                if (kb < G::kWloTmemKB) {  // += W_lo . h_hi into the cross-term columns: W_lo from TMEM ...
+                  cl_umma_ts(t_d + NS, t_alo + (uint32_t)(kb * 32 + ks * 8), d_h, idesc_n, 1u);
+                } else {                   // ... or from shared memory
+                  const uint64_t d_wlo = d_wlo0 + (uint64_t)((((kb - G::kWloTmemKB) * kClWloKb) + ks * 32) >> 4);
+                  umma_f16(t_d + NS, d_wlo, d_h, idesc_n, 1u);
+                }
               }
             }
           }
@@ -439,31 +435,39 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
 #endif
         }
 #ifdef VOCR_LSTM_PROF
-        if (blockIdx.x == 3) printf("lstm cluster mma thread: steps %d  wait-full %lld  issue %lld\n", tm - 1, mf_wait, mf_issue);
+        if (blockIdx.x == 3) printf("lstm cluster<%d> mma thread: steps %d  wait-full %lld  issue %lld\n", NS, tm - 1, mf_wait, mf_issue);
 #endif
       }
       __syncwarp();
     } else {
       // ===================================== input-projection loader warp ========================================
-      // lane = sample: 4 gate rows x US units of xproj[t, b, dir] -> xs[sample][gate*32 + unit], one step ahead
-      const int n = lane, b = b_base + n;
-      const int len = (b < a.B) ? min(a.lens[b], a.Tmax) : 0;
+      // lane = sample (and sample + 32): 4 gate rows x US units of xproj[t, b, dir] -> xs[sample][gate*32 + unit], one
+      // step ahead
       const int nch = (nu * 4 + 15) / 16;  // 16-byte chunks per gate row (H % 4 == 0)
+      int len[NP];
+#pragma unroll
+      for (int ps = 0; ps < NP; ++ps) {
+        const int b = b_base + 32 * ps + lane;
+        len[ps] = (b < a.B) ? min(a.lens[b], a.Tmax) : 0;
+      }
       for (int k = 0; k < tm; ++k) {
         if (k > 0) {
           mbar_wait_or_trap(xs_free, n_xsfree & 1u);
           ++n_xsfree;
         }
-        if (k < len) {
-          const int tt = dir == 0 ? k : len - 1 - k;
-          const float* src = a.xproj + (((size_t)tt * a.B + b) * 2 + dir) * 4 * H + u0;
-          float* dst = xs + n * kClXsLd;
-          for (int gg = 0; gg < 4; ++gg)
-            for (int c = 0; c < nch; ++c)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + gg * 32 + c * 4)),
-                           "l"(src + (size_t)gg * H + c * 4)
-                           : "memory");
-        }
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps)
+          if (k < len[ps]) {
+            const int n = 32 * ps + lane;
+            const int tt = dir == 0 ? k : len[ps] - 1 - k;
+            const float* src = a.xproj + (((size_t)tt * a.B + b_base + n) * 2 + dir) * 4 * H + u0;
+            float* dst = xs + n * G::kXsLd;
+            for (int gg = 0; gg < 4; ++gg)
+              for (int c = 0; c < nch; ++c)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + gg * 32 + c * 4)),
+                             "l"(src + (size_t)gg * H + c * 4)
+                             : "memory");
+          }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xs_full)) : "memory");
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
     __syncthreads();
     if (item + n_clusters < a.n_items) {
       cl_cluster_sync();
-      for (int i = tid; i < (int)(kClTileBytes / 16); i += kClThreads) reinterpret_cast<uint4*>(Ht)[i] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < (int)(G::kTileBytes / 16); i += kClThreads) reinterpret_cast<uint4*>(Ht)[i] = make_uint4(0, 0, 0, 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
@@ -494,14 +498,17 @@ __global__ void __launch_bounds__(kClThreads, 1) bilstm_fwd_cluster_kernel(LstmC
 
 using namespace vocr;
 
+static int lstm_cl_samples(int B) { return B >= 128 ? 64 : 32; }  // samples per cluster work item
+
 static int lstm_cl_geometry(int B, int H, LstmClArgs* a, size_t* smem) {
   if (H < 1 || H > 64 * kClMaxKB || (H % 4) != 0) return VOCR_INVALID_VALUE;
+  const int ns = lstm_cl_samples(B);
   a->KB = ceil_div(H, 64);
   a->US = 8 * ceil_div(H, 8 * kClSize);  // unit slots per CTA: a multiple of 8 (one 16-byte chunk), at most 32
   a->NSL = ceil_div(H, a->US);
-  a->NG = ceil_div(B, kClN);
+  a->NG = ceil_div(B, ns);
   a->n_items = 2 * a->NG;
-  *smem = (size_t)kClMaxKB * kClWloKb + kClTileBytes + kClXsBytes + 64 + 1024 /*alignment*/;
+  *smem = ns == 64 ? ClGeom<64>::kSmem : ClGeom<32>::kSmem;
   return VOCR_OK;
 }
 
@@ -522,27 +529,16 @@ size_t lstm_tc_fwd_workspace_bytes(int T, int B, int H) {
   LstmClArgs a;
   size_t smem;
   if (!lstm_tc_enabled() || lstm_cl_geometry(B, H, &a, &smem) != VOCR_OK) return 0;
-  return 1024 + (size_t)lstm_cl_clusters(a.n_items) * kClSize * 2 * 4096;
+  return 1024 + (size_t)lstm_cl_clusters(a.n_items) * kClSize * 2 * ClGeom<64>::kStageBytes;
 }
 
-int lstm_tc_fwd_launch(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates, float* cst,
-                       int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  LstmClArgs a{};
-  size_t smem;
-  int st = lstm_cl_geometry(B, H, &a, &smem);
-  if (st != VOCR_OK) return -1;  // shape not covered by this kernel: the caller uses the mma.sync kernel
-  a.xproj = xproj; a.whh = whh; a.lens = lens; a.out = out; a.gates = gates; a.cst = cst;
-  a.T = T; a.B = B; a.H = H; a.Tmax = Tmax;
-  if ((reinterpret_cast<uintptr_t>(xproj) & 15) != 0) return -1;
-  const int nc = lstm_cl_clusters(a.n_items);
-  const uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
-  const size_t need = (size_t)nc * kClSize * 2 * 4096;
-  if ((w - reinterpret_cast<uintptr_t>(workspace)) + need > workspace_bytes) return VOCR_INVALID_VALUE;
-  a.stage = reinterpret_cast<unsigned char*>(w);
+template <int NS>
+static int lstm_cl_launch(const LstmClArgs& a, int nc, size_t smem, cudaStream_t stream) {
   static DeviceLatch latch;
   if (latch.need()) {
-    if (cudaFuncSetAttribute(bilstm_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(bilstm_fwd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    if (cudaFuncSetAttribute(bilstm_fwd_cluster_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(bilstm_fwd_cluster_kernel<NS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     latch.set();
   }
@@ -558,6 +554,23 @@ int lstm_tc_fwd_launch(const float* xproj, const float* whh, const int32_t* lens
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, bilstm_fwd_cluster_kernel, a) != cudaSuccess) return VOCR_EXECUTION_FAILED;
+  if (cudaLaunchKernelEx(&cfg, bilstm_fwd_cluster_kernel<NS>, a) != cudaSuccess) return VOCR_EXECUTION_FAILED;
   return VOCR_OK;
+}
+
+int lstm_tc_fwd_launch(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates, float* cst,
+                       int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LstmClArgs a{};
+  size_t smem;
+  int st = lstm_cl_geometry(B, H, &a, &smem);
+  if (st != VOCR_OK) return -1;  // shape not covered by this kernel: the caller uses the mma.sync kernel
+  a.xproj = xproj; a.whh = whh; a.lens = lens; a.out = out; a.gates = gates; a.cst = cst;
+  a.T = T; a.B = B; a.H = H; a.Tmax = Tmax;
+  if ((reinterpret_cast<uintptr_t>(xproj) & 15) != 0) return -1;
+  const int nc = lstm_cl_clusters(a.n_items);
+  const uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  const size_t need = (size_t)nc * kClSize * 2 * ClGeom<64>::kStageBytes;
+  if ((w - reinterpret_cast<uintptr_t>(workspace)) + need > workspace_bytes) return VOCR_INVALID_VALUE;
+  a.stage = reinterpret_cast<unsigned char*>(w);
+  return lstm_cl_samples(B) == 64 ? lstm_cl_launch<64>(a, nc, smem, stream) : lstm_cl_launch<32>(a, nc, smem, stream);
 }
