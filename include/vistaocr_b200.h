@@ -96,7 +96,8 @@ int vocr_colsum_f32(const float* x, long long rows, int cols, int ld, float* out
  *   wd[(ky,kx,co),ci] = W[co,ci,2-ky,2-kx] (data gradient); either output may be NULL.
  * vocr_conv3x3_fwd_f32: z[B,H,W,Cout] = conv3x3_pad1(x[B,H,W,Cin]; wk) + bias.  If stats != NULL the per-channel
  *   sum and sum of squares of z are ACCUMULATED into stats[0:Cout], stats[Cout:2Cout] (float64; caller zeroes).
- *   The data gradient is the same call with (x := dz, wk := wd, Cin/Cout swapped, bias = stats = NULL).
+ *   zmax (optional device float the caller zeroes) receives max |z| (see vocr_tc_conv3x3_fwd_f16).
+ *   The data gradient is the same call with (x := dz, wk := wd, Cin/Cout swapped, bias = stats = zmax = NULL).
  * vocr_conv3x3_wgrad_f32: dw[Cout,Cin,3,3] = sum over pixels (state_dict layout, deterministic split-K).
  * vocr_rds_fwd_f32: rapid-downsample stage, y[B,H/2,W/2,16] = maxpool2x2(relu(conv3x3(x[B,H,W,Cin]; wk[9*Cin,16])
  *   + bias)); arg (uint8 per output, may be NULL) records the winning window position for the backward pass.
@@ -105,7 +106,7 @@ int vocr_colsum_f32(const float* x, long long rows, int cols, int ld, float* out
  * ---------------------------------------------------------------------------------------------------------- */
 int vocr_conv_weight_layout_f32(const float* w, int Cin, int Cout, float* wk, float* wd, vocr_stream_t stream);
 int vocr_conv3x3_fwd_f32(const float* x, const float* wk, const float* bias, float* z, int B, int H, int W, int Cin,
-                         int Cout, double* stats, vocr_stream_t stream);
+                         int Cout, double* stats, float* zmax, vocr_stream_t stream);
 size_t vocr_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout);
 int vocr_conv3x3_wgrad_f32(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout,
                            void* workspace, size_t workspace_bytes, vocr_stream_t stream);
@@ -122,7 +123,7 @@ int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const
  *   stats updated in place (unbiased variance); else running stats.  Emits scale = gamma*invstd,
  *   shift = beta - mean*scale and (optionally) save_mean / save_invstd for the backward pass.
  * vocr_bn_relu_apply_f32: a[b*sB + y*sH + x*sW + c] = relu(z[b,y,x,c]*scale[c] + shift[c])  (strides in elements,
- *   c contiguous) - the last CNN block writes the [T,B,h*C] sequence layout directly (replaces the
+ *   c contiguous; a may be NULL when only the FP16 pair planes are wanted - inference, consumer = a tensor-core conv) - the last CNN block writes the [T,B,h*C] sequence layout directly (replaces the
  *   permute+contiguous of cnnlstm.py:276).  a_hi / a_lo (both or neither; same layout as a) optionally receive the
  *   TF32 split planes the tensor-core conv of the next block reads (saves a vocr_split_tf32_f32 pass); dz_hi / dz_lo
  *   of vocr_bn_relu_bwd_f32 likewise.

@@ -29,7 +29,7 @@ PROTOTYPES = {
                               c_int, c_p]),
     "vocr_colsum_f32": (c_int, [c_p, c_ll, c_int, c_int, c_p, c_int, c_p]),
     "vocr_conv_weight_layout_f32": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p]),
-    "vocr_conv3x3_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p]),
+    "vocr_conv3x3_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
     "vocr_conv3x3_wgrad_workspace_size": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
     "vocr_conv3x3_wgrad_f32": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_sz, c_p]),
     "vocr_rds_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),

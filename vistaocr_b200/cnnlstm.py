@@ -162,7 +162,8 @@ class CnnOcrModel(nn.Module):
             last = k == n_blocks - 1
             feat = ops.conv_bn_relu(feat, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                     bn.running_var, training, bn.momentum, bn.eps, seq_layout=last,
-                                    planes=not last and not _CONV_PLAN[k][1])
+                                    planes=not last and not _CONV_PLAN[k][1],
+                                    allow_planes_only=not last and not _CONV_PLAN[k][1] and _CONV_PLAN[k + 1][0] % 64 == 0)
             if training:
                 bn.num_batches_tracked += 1
             if _CONV_PLAN[k][1]:

@@ -87,7 +87,7 @@ bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ scal
     r.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
     r.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
     const long long o = b * sB + y * sH + x * sW + (long long)c4 * 4;
-    *reinterpret_cast<float4*>(a + o) = r;
+    if (a) *reinterpret_cast<float4*>(a + o) = r;
     if (a_hi) {  // TF32 (hi, lo) planes for the tensor-core conv that consumes this activation
       float4 h, l;
       h.x = tf32_rna(r.x); l.x = tf32_rna(r.x - h.x);
@@ -285,8 +285,8 @@ extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long P = (long long)B * H * W;
   if (P == 0) return VOCR_OK;
-  VOCR_REQUIRE(z && scale && shift && a && C > 0 && C % 4 == 0);
-  VOCR_REQUIRE(aligned16(z) && aligned16(a) && aligned16(scale) && aligned16(shift));
+  VOCR_REQUIRE(z && scale && shift && (a || a_hi16) && C > 0 && C % 4 == 0);  // a may be NULL: planes only
+  VOCR_REQUIRE(aligned16(z) && (!a || aligned16(a)) && aligned16(scale) && aligned16(shift));
   VOCR_REQUIRE(sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
   const long long total = P * (C / 4);
   const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));

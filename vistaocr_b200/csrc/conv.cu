@@ -135,6 +135,8 @@ struct ConvFwdEpilogue {
   int N;
   const float* bias;
   double* stats;  // [2*N] or nullptr
+  unsigned* zmax; // optional: max |z| (bit pattern of the non-negative float, atomicMax)
+  float vmax;
   float* s_sum;   // shared [BN], s_sq shared [BN] (zeroed by the kernel)
   float* s_sq;
   int n0;
@@ -142,6 +144,7 @@ struct ConvFwdEpilogue {
   __device__ __forceinline__ void begin() {
 #pragma unroll
     for (int j = 0; j < 4 * (BN / 64); ++j) cs[j] = cq[j] = 0.f;
+    vmax = 0.f;
   }
   __device__ __forceinline__ void operator()(int m, int n, float4 v, int j) {
     if (m >= P || n >= N) return;
@@ -153,6 +156,7 @@ struct ConvFwdEpilogue {
         if (bias) r[c] += __ldg(bias + n + c);
         cs[4 * j + c] += r[c];
         cq[4 * j + c] = fmaf(r[c], r[c], cq[4 * j + c]);
+        vmax = fmaxf(vmax, fabsf(r[c]));
       }
     }
     if ((N & 3) == 0) {
@@ -164,6 +168,10 @@ struct ConvFwdEpilogue {
     }
   }
   __device__ __forceinline__ void finish() {
+    if (zmax) {
+      const float m = warp_max(vmax);
+      if ((threadIdx.x & 31) == 0) atomicMax(zmax, __float_as_uint(m));
+    }
     if (!stats) return;
     const int tx = threadIdx.x & 15;
 #pragma unroll
@@ -187,11 +195,11 @@ struct ConvFwdEpilogue {
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads)
-conv3x3_fwd_kernel(ConvALoad la, BLoadContigN lb, float* z, const float* bias, double* stats, int N) {
+conv3x3_fwd_kernel(ConvALoad la, BLoadContigN lb, float* z, const float* bias, double* stats, unsigned* zmax, int N) {
   __shared__ float s_sum[BN], s_sq[BN];
   for (int i = threadIdx.x; i < BN; i += kGemmThreads) s_sum[i] = s_sq[i] = 0.f;
   ConvFwdEpilogue<BN> ep;
-  ep.z = z; ep.P = la.P; ep.N = N; ep.bias = bias; ep.stats = stats; ep.s_sum = s_sum; ep.s_sq = s_sq;
+  ep.z = z; ep.P = la.P; ep.N = N; ep.bias = bias; ep.stats = stats; ep.zmax = zmax; ep.s_sum = s_sum; ep.s_sq = s_sq;
   // pixel tiles in grid.x (up to 2^31 - 1 of them: 512 lines x 30 x 1200 px is 144k tiles), channel tiles in grid.y
   ep.n0 = blockIdx.y * BN;
   ep.begin();
@@ -450,7 +458,7 @@ extern "C" int vocr_conv_weight_layout_f32(const float* w, int Cin, int Cout, fl
 
 // x [B,H,W,Cin] NHWC, wk [9*Cin,Cout], z [B,H,W,Cout]; stats (optional) double[2*Cout] is ACCUMULATED into.
 extern "C" int vocr_conv3x3_fwd_f32(const float* x, const float* wk, const float* bias, float* z, int B, int H,
-                                    int W, int Cin, int Cout, double* stats, vocr_stream_t stream_) {
+                                    int W, int Cin, int Cout, double* stats, float* zmax, vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0);
   const long long P = (long long)B * H * W;
@@ -462,10 +470,10 @@ extern "C" int vocr_conv3x3_fwd_f32(const float* x, const float* wk, const float
   lb.p = wk; lb.cols = Cout; lb.ld = Cout; lb.vec = (Cout % 4 == 0) && aligned16(wk);
   if (Cout <= 64) {
     dim3 grid((unsigned)ceil_div64(P, kGemmBM), ceil_div(Cout, 64));
-    conv3x3_fwd_kernel<64><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, Cout);
+    conv3x3_fwd_kernel<64><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, reinterpret_cast<unsigned*>(zmax), Cout);
   } else {
     dim3 grid((unsigned)ceil_div64(P, kGemmBM), ceil_div(Cout, 128));
-    conv3x3_fwd_kernel<128><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, Cout);
+    conv3x3_fwd_kernel<128><<<grid, kGemmThreads, 0, stream>>>(la, lb, z, bias, stats, reinterpret_cast<unsigned*>(zmax), Cout);
   }
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;

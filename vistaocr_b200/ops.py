@@ -217,9 +217,10 @@ def linear(x, w, b=None, relu=False, x_bound=None):
 # ---------------------------------------------------------------------------------------------------------------
 # conv3x3 + BatchNorm + ReLU block
 # ---------------------------------------------------------------------------------------------------------------
-def _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, stats):
+def _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, stats, zmax=None):
     z = torch.empty((B, H, W, Cout), dtype=F32, device=x.device)
-    st = lib().vocr_conv3x3_fwd_f32(ptr(x), ptr(wk), ptr(bias), ptr(z), B, H, W, Cin, Cout, ptr(stats), stream())
+    st = lib().vocr_conv3x3_fwd_f32(ptr(x), ptr(wk), ptr(bias), ptr(z), B, H, W, Cin, Cout, ptr(stats), ptr(zmax),
+                                    stream())
     check(st, "vocr_conv3x3_fwd_f32")
     return z
 
@@ -325,7 +326,9 @@ def conv3x3(x, weight, bias, x_op=None, zmax=None):
         wn = Operand(weight.detach().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
         return _tc_conv_fwd(x_op.split(), wn.split(), bias, B, H, W, Cin, Cout), x_op
     wk, _ = _weight_layout(_c(weight.detach()), True, False)
-    return _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, None), x_op
+    if zmax is not None:
+        zmax.measured = True
+    return _conv_fwd(x, wk, bias, B, H, W, Cin, Cout, None, zmax), x_op
 
 
 def conv3x3_dgrad(dz, weight, dz_op=None):
@@ -377,7 +380,7 @@ class _ConvBNReLU(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps, seq_layout,
-                planes=True):
+                planes=True, allow_planes_only=False):
         x = _c(x)
         _lib.require_cuda(x, "x", F32)
         B, H, W, Cin = x.shape
@@ -406,7 +409,7 @@ class _ConvBNReLU(torch.autograd.Function):
             a = torch.empty((W, B, H * Cout), dtype=F32, device=dev)
             strides = (H * Cout, Cout, B * H * Cout)
         else:
-            a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
+            a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)  # (not written in the planes-only case below)
             strides = (H * W * Cout, W * Cout, Cout)
         # the next tensor-core conv reads this activation as TF32 (hi, lo) planes: let the apply kernel write them
         want_split = USE_TC and not USE_F16 and not seq_layout and Cout % 32 == 0 and planes
@@ -418,7 +421,12 @@ class _ConvBNReLU(torch.autograd.Function):
         a_hi16 = torch.empty(a.shape, dtype=torch.float16, device=dev) if want16 else None
         a_lo16 = torch.empty(a.shape, dtype=torch.float16, device=dev) if want16 else None
         pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
-        st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), ptr(a), ptr(a_hi), ptr(a_lo), B, H, W, Cout,
+        # inference with a tensor-core conv as the only consumer (`planes`): that conv reads the planes, nobody reads the
+        # fp32 activation - do not write it (the returned tensor then only carries the shape and the operand planes)
+        planes_only = allow_planes_only and want16 and not training and not torch.is_grad_enabled() and \
+            not x.requires_grad
+        st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), None if planes_only else ptr(a), ptr(a_hi),
+                                          ptr(a_lo), B, H, W, Cout,
                                           strides[0], strides[1], strides[2], ptr(a_hi16), ptr(a_lo16),
                                           ptr(aux) if want16 else None, ptr(pstate), stream())
         check(st, "vocr_bn_relu_apply_f32")
@@ -466,15 +474,17 @@ class _ConvBNReLU(torch.autograd.Function):
             dx, dz_op = conv3x3_dgrad(dz, weight, dz_op)
         dw = conv3x3_wgrad(x, dz, ctx.x_op, dz_op)
         ctx.x_op = None
-        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 def conv_bn_relu(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5,
-                 seq_layout=False, planes=True):
+                 seq_layout=False, planes=True, allow_planes_only=False):
     """planes: the consumer is another tensor-core conv, so the apply kernel also emits the operand planes (pass False
-    when a pooling layer follows - the planes would go unread)."""
+    when a pooling layer follows - the planes would go unread).  allow_planes_only: the caller guarantees that a
+    tensor-core conv of this module is the ONLY consumer; in inference (eval statistics, no autograd) the fp32 activation
+    is then not written at all - the returned tensor carries the shape and the planes, its values are undefined."""
     return _ConvBNReLU.apply(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps,
-                             seq_layout, planes)
+                             seq_layout, planes, allow_planes_only)
 
 
 class _RapidDS(torch.autograd.Function):
