@@ -150,14 +150,50 @@ def synth_ctc_case(T, A, L, B, seed, dev):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML (pynvml) every 5 ms when available, else
+    nvidia-smi (the recipe's clocks line) as fast as it returns."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.samples, self._stop, self._t, self.how = index, [], threading.Event(), None, "nvidia-smi"
+
+    def _nvml_handle(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            return None, None
 
     def _run(self):
+        nv, h = self._nvml_handle()
+        if nv is not None:
+            self.how = "nvml"
+            bits = [getattr(nv, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                                                  "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap")]
+            if not any(bits):  # older NVML naming
+                bits = [getattr(nv, n, 0) for n in ("nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                                                      "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
+            try:
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            while not self._stop.is_set():
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append([str(sm), str(mx)] + ["Active" if (b and (r & b)) else "Not Active" for b in bits])
+                except Exception:
+                    pass
+                self._stop.wait(0.005)
+            return
         while not self._stop.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -179,10 +215,9 @@ class ClockSampler:
     def summary(self):
         sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v == "Active"})
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(self.NAMES, s[2:6]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.how}
 
 
 class Ctx:
