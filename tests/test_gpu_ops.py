@@ -206,6 +206,14 @@ def test_bilstm_layer(cuda, T, B, D, H, ragged):
         close(G[n].grad, R[n].grad, what="lstm d" + n)
 
 
+@pytest.mark.parametrize("T,B,D,H", [(9, 40, 8, 512), (11, 64, 8, 40), (6, 5, 8, 200), (7, 33, 12, 16)])
+def test_bilstm_layer_cluster_backward(cuda, monkeypatch, T, B, D, H):
+    """The opt-in cluster-resident tcgen05 backward recurrence (csrc/lstm_tc.cu, VOCR_LSTM_TC_BWD=1; measured slower than
+    the default kernel, kept as a checked alternative) meets the same bounds."""
+    monkeypatch.setenv("VOCR_LSTM_TC_BWD", "1")
+    test_bilstm_layer(cuda, T, B, D, H, True)
+
+
 def test_clamp_adam_matches_torch(cuda):
     from vistaocr_b200 import ops
     g = torch.Generator().manual_seed(3)

@@ -763,6 +763,10 @@ size_t lstm_tc_fwd_workspace_bytes(int T, int B, int H);
 int lstm_tc_fwd_launch(const float* xproj, const float* whh, const int32_t* lens, float* out, float* gates, float* cst,
                        int T, int B, int H, int Tmax, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 bool lstm_tc_enabled();
+size_t lstm_tc_bwd_workspace_bytes(int T, int B, int H);
+int lstm_tc_bwd_launch(const float* dout, const float* whh, const int32_t* lens, const float* gates, const float* cst,
+                       float* dgates, float* absmax, int T, int B, int H, int Tmax, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
 
 extern "C" size_t vocr_bilstm_workspace_size(int T, int B, int H, int backward) {
   LstmArgs a;
@@ -770,7 +774,7 @@ extern "C" size_t vocr_bilstm_workspace_size(int T, int B, int H, int backward) 
   int gy, variant;
   if (T < 0 || lstm_geometry(B, H, &a, &smem, &gy, backward != 0, &variant) != VOCR_OK) return 0;
   size_t need = 256 + lstm_flag_bytes(a, backward != 0) + lstm_xchg_bytes(a, backward != 0);
-  if (!backward) need = std::max(need, lstm_tc_fwd_workspace_bytes(T, B, H));
+  need = std::max(need, backward ? lstm_tc_bwd_workspace_bytes(T, B, H) : lstm_tc_fwd_workspace_bytes(T, B, H));
   return need;
 }
 
@@ -845,5 +849,10 @@ extern "C" int vocr_bilstm_bwd_f32(const float* dout, const float* whh, const in
   a.gates = const_cast<float*>(gates); a.cst = const_cast<float*>(cst);
   a.absmax = dgates_absmax;
   a.T = T; a.B = B; a.H = H; a.Tmax = Tmax;
+  if (lstm_tc_enabled()) {  // cluster-resident tcgen05 kernel (lstm_tc.cu); -1 = shape it does not cover
+    const int st = lstm_tc_bwd_launch(dout, whh, lens, gates, cst, dgates, dgates_absmax, T, B, H, Tmax, workspace,
+                                      workspace_bytes, stream);
+    if (st != -1) return st;
+  }
   return lstm_launch(true, a, workspace, workspace_bytes, stream);
 }

@@ -1,6 +1,7 @@
 // Shared device/host helpers of the tcgen05 / TMA kernels (tc_gemm.cu, tc_conv.cu).
 #pragma once
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "pair_f16.cuh"
 
@@ -15,6 +16,35 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- thread-block clusters: CTAs that work on neighbouring output tiles share operand tiles ---------------------------
+// A tile that several CTAs of a cluster need is fetched ONCE from L2: each of them loads 1/n-th of it and the TMA unit
+// multicasts that part into the same shared-memory offset of every CTA in `mask` (and signals the mbarrier at the same
+// offset there), so the L2 -> SM traffic of the tile is divided by n.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -102,6 +132,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&t)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// VOCR_TC_CLUSTER=0 launches every tensor-core kernel without clusters (A/B measurements; same results either way)
+inline bool tc_clusters_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VOCR_TC_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 // ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ---------------------------

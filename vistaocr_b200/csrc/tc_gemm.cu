@@ -40,8 +40,78 @@ struct TcGemmParams {
   const int* exp_b;
   int single;        // 1 = one product per k-step on the hi planes only (reduced-precision mode: fp16 operands, fp32
                      //     accumulation; the lo planes are neither loaded nor multiplied)
+  int cm, cn;        // thread-block cluster = cm x cn neighbouring output tiles (1 or 2 each); see TcClusterPos
 };
 constexpr int kTcChunk = 8;  // k-blocks accumulated in TMEM before the epilogue warps drain them into fp32 registers
+
+// Cluster of cm x cn output tiles (CTA rank r -> tile row rm = r / cn, tile column rn = r % cn of the cluster's
+// super-tile).  The cn CTAs of a tile row need the same A tile and the cm CTAs of a tile column the same B tile:
+// CTA (rm, rn) fetches part rn of its A tile and part rm of its B tile and multicasts them (tc_common.cuh), so per
+// k-block a CTA pulls 1/cn of A and 1/cm of B through its own L2 port instead of both tiles - at 2 x 2 half the bytes.
+// A CTA may refill a stage once every CTA its parts land in has retired the MMAs that read the stage: the MMA warp's
+// commit arrives on `empty` of every CTA in mask_a | mask_b (the senders into this CTA), and `empty` counts cm + cn - 1.
+struct TcClusterPos {
+  int size, rm, rn;
+  uint16_t mask_a, mask_b;
+};
+__device__ __forceinline__ TcClusterPos tc_cluster_pos(const TcGemmParams& p) {
+  TcClusterPos c;
+  c.size = p.cm * p.cn;
+  const int r = c.size > 1 ? (int)tc_cluster_rank() : 0;
+  c.rm = r / p.cn;
+  c.rn = r - c.rm * p.cn;
+  c.mask_a = (uint16_t)(((1u << p.cn) - 1u) << (c.rm * p.cn));
+  c.mask_b = 0;
+  for (int i = 0; i < p.cm; ++i) c.mask_b |= (uint16_t)(1u << (i * p.cn + c.rn));
+  return c;
+}
+
+// One operand tile (128 rows of the M or N dimension x one k-block) of both planes: part `part` of `parts`, multicast
+// to `mask` when the tile is shared.  K-major: box {BK k, 128 / parts rows}; MN-major: boxes {32|64 m, BK k rows}.
+template <bool F16>
+__device__ __forceinline__ void tc_load_operand(unsigned char* hi, unsigned char* lo, const CUtensorMap* map_hi,
+                                                const CUtensorMap* map_lo, uint64_t* full, int mn, int parts, int part,
+                                                uint16_t mask, int k0, int r0, int single) {
+  using E = TcElem<F16>;
+  if (!mn) {
+    if (parts == 1) {
+      tma_load_2d(hi, map_hi, full, k0, r0);
+      if (!single) tma_load_2d(lo, map_lo, full, k0, r0);
+    } else {
+      const int rows = kTcBM / parts;
+      const uint32_t off = (uint32_t)(part * rows) * 128u;
+      tma_load_2d_mc(hi + off, map_hi, full, k0, r0 + part * rows, mask);
+      if (!single) tma_load_2d_mc(lo + off, map_lo, full, k0, r0 + part * rows, mask);
+    }
+  } else {
+    const int per = (kTcBM / E::kMnBox) / parts;
+    for (int j = part * per; j < (part + 1) * per; ++j) {
+      if (parts == 1) {
+        tma_load_2d(hi + j * E::kMnBoxBytes, map_hi, full, r0 + E::kMnBox * j, k0);
+        if (!single) tma_load_2d(lo + j * E::kMnBoxBytes, map_lo, full, r0 + E::kMnBox * j, k0);
+      } else {
+        tma_load_2d_mc(hi + j * E::kMnBoxBytes, map_hi, full, r0 + E::kMnBox * j, k0, mask);
+        if (!single) tma_load_2d_mc(lo + j * E::kMnBoxBytes, map_lo, full, r0 + E::kMnBox * j, k0, mask);
+      }
+    }
+  }
+}
+// all four tiles of a stage (A_hi, A_lo, B_hi, B_lo); `full` expects the whole stage whoever delivers it
+template <bool F16>
+__device__ __forceinline__ void tc_load_stage(unsigned char* st, uint64_t* full, const CUtensorMap* ma_hi,
+                                              const CUtensorMap* ma_lo, const CUtensorMap* mb_hi,
+                                              const CUtensorMap* mb_lo, const TcGemmParams& p, const TcClusterPos& c,
+                                              int k0, int m0, int n0) {
+  mbar_arrive_expect_tx(full, p.single ? kTcStageBytes / 2 : kTcStageBytes);
+  tc_load_operand<F16>(st, st + kTcTileBytes, ma_hi, ma_lo, full, p.a_mn, p.cn, c.rn, c.mask_a, k0, m0, p.single);
+  tc_load_operand<F16>(st + 2 * kTcTileBytes, st + 3 * kTcTileBytes, mb_hi, mb_lo, full, p.b_mn, p.cm, c.rm, c.mask_b,
+                       k0, n0, p.single);
+}
+// frees a stage: locally, or in every CTA whose loads land in this CTA's stage
+__device__ __forceinline__ void tc_release_stage(uint64_t* empty, const TcClusterPos& c) {
+  if (c.size > 1) umma_commit_mc(empty, (uint16_t)(c.mask_a | c.mask_b));
+  else umma_commit(empty);
+}
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -64,7 +134,8 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+  const TcClusterPos cp = tc_cluster_pos(p);  // grid = (n tiles, m tiles) padded to the cluster shape (cn, cm)
+  const int m0 = ((int)(blockIdx.y / p.cm) * p.cm + cp.rm) * kTcBM, n0 = ((int)(blockIdx.x / p.cn) * p.cn + cp.rn) * kTcBN;
   using E = TcElem<F16>;
   constexpr int BK = E::kBK;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -72,7 +143,7 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)(p.cm + p.cn - 1));
     }
     mbar_init(tmem_full_bar, 1);
     mbar_fence_init();
@@ -85,6 +156,7 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cm * p.cn > 1) tc_cluster_sync();  // every CTA's barriers exist before a peer can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -95,29 +167,8 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const int s = kb % kTcStages;
         const uint32_t ph = (uint32_t)(kb / kTcStages) & 1u;
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
-        unsigned char* st = smem + (size_t)s * kTcStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], p.single ? kTcStageBytes / 2 : kTcStageBytes);
-        const int k0 = kb * BK;
-        if (!p.a_mn) {
-          tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
-          if (!p.single) tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
-        } else {
-          for (int j = 0; j < kTcBM / E::kMnBox; ++j) {                        // boxes {32|64 m, BK k rows}
-            tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
-            if (!p.single)
-              tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
-          }
-        }
-        if (!p.b_mn) {
-          tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
-          if (!p.single) tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
-        } else {
-          for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
-            tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
-            if (!p.single)
-              tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
-          }
-        }
+        tc_load_stage<F16>(smem + (size_t)s * kTcStageBytes, &full_bar[s], &map_a_hi, &map_a_lo, &map_b_hi, &map_b_lo, p,
+                           cp, kb * BK, m0, n0);
       }
     }
   } else if (warp == 1) {
@@ -157,7 +208,7 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           E::mma(tmem_base + (uint32_t)(kb % kTcHiAcc) * kTcBN, a_hi, b_hi, idesc,
                  (kb >= kTcHiAcc || ks > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
+        tc_release_stage(&empty_bar[s], cp);  // frees the stage once the MMAs above have read it
       }
       umma_commit(tmem_full_bar);    // accumulator complete
     }
@@ -227,6 +278,7 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cm * p.cn > 1) tc_cluster_sync();  // no CTA leaves while a peer's commit could still arrive here
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -246,7 +298,7 @@ template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                          TcGemmParams p, int tiles_n, int num_tiles) {
+                          TcGemmParams p, int super_n, int num_super) {
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) &
                                                          ~uintptr_t(1023));
@@ -261,11 +313,14 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
   constexpr int BK = E::kBK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
+  // a cluster walks over super-tiles of cm x cn output tiles; its CTAs run the same trip counts
+  const TcClusterPos cp = tc_cluster_pos(p);
+  const int cluster_id = blockIdx.x / cp.size, n_clusters = gridDim.x / cp.size;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)(p.cm + p.cn - 1));
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -276,6 +331,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.cm * p.cn > 1) tc_cluster_sync();  // every CTA's barriers exist before a peer can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -283,35 +339,14 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
     // ================================ TMA producer ================================
     if (lane == 0) {
       int it = 0;  // k-blocks issued so far (the stage ring runs across tiles)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * kTcBM, n0 = (tile % tiles_n) * kTcBN;
+      for (int st = cluster_id; st < num_super; st += n_clusters) {
+        const int m0 = ((st / super_n) * p.cm + cp.rm) * kTcBM, n0 = ((st % super_n) * p.cn + cp.rn) * kTcBN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kTcStages;
           const uint32_t ph = (uint32_t)(it / kTcStages) & 1u;
           mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
-          unsigned char* st = smem + (size_t)s * kTcStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], p.single ? kTcStageBytes / 2 : kTcStageBytes);
-          const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
-            if (!p.single) tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
-          } else {
-            for (int j = 0; j < kTcBM / E::kMnBox; ++j) {
-              tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
-              if (!p.single)
-                tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
-            }
-          }
-          if (!p.b_mn) {
-            tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
-            if (!p.single) tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
-          } else {
-            for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
-              tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
-              if (!p.single)
-                tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
-            }
-          }
+          tc_load_stage<F16>(smem + (size_t)s * kTcStageBytes, &full_bar[s], &map_a_hi, &map_a_lo, &map_b_hi, &map_b_lo, p,
+                             cp, kb * BK, m0, n0);
         }
       }
     }
@@ -325,7 +360,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
       const uint32_t a_sbo = p.a_mn ? E::kMnSbo : 1024u, b_sbo = p.b_mn ? E::kMnSbo : 1024u;
       const uint32_t a_lt = p.a_mn ? E::kMnLayout : 2u, b_lt = p.b_mn ? E::kMnLayout : 2u;
       int it = 0, j = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      for (int st = cluster_id; st < num_super; st += n_clusters, ++j) {
         const int set = j & 1;
         mbar_wait_or_trap(&acc_empty[set], ((uint32_t)(j >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -349,7 +384,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             }
             E::mma(tmem_hi, a_hi, b_hi, idesc, acc);
           }
-          umma_commit(&empty_bar[s]);
+          tc_release_stage(&empty_bar[s], cp);
         }
         umma_commit(&acc_full[set]);
       }
@@ -360,9 +395,9 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
     const int out_shift = F16 ? -(__ldg(p.exp_a) + __ldg(p.exp_b)) : 0;
     int j = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+    for (int st = cluster_id; st < num_super; st += n_clusters, ++j) {
       const int set = j & 1;
-      const int m0 = (tile / tiles_n) * kTcBM, n0 = (tile % tiles_n) * kTcBN;
+      const int m0 = ((st / super_n) * p.cm + cp.rm) * kTcBM, n0 = ((st % super_n) * p.cn + cp.rn) * kTcBN;
       mbar_wait_or_trap(&acc_full[set], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const int m = m0 + lane_grp * 32 + lane;
@@ -413,6 +448,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cm * p.cn > 1) tc_cluster_sync();  // no CTA leaves while a peer's commit could still arrive here
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -442,7 +478,8 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+  const TcClusterPos cp = tc_cluster_pos(p);  // grid = (n tiles, m tiles) padded to the cluster shape (cn, cm)
+  const int m0 = ((int)(blockIdx.y / p.cm) * p.cm + cp.rm) * kTcBM, n0 = ((int)(blockIdx.x / p.cn) * p.cn + cp.rn) * kTcBN;
   using E = TcElem<F16>;
   constexpr int BK = E::kBK;
   const int total_kb = (p.K + BK - 1) / BK;
@@ -455,7 +492,7 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)(p.cm + p.cn - 1));
     }
     for (int a = 0; a < kTcHiAcc; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -467,6 +504,7 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.cm * p.cn > 1) tc_cluster_sync();  // every CTA's barriers exist before a peer can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -477,29 +515,8 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int s = i % kTcStages;
         const uint32_t ph = (uint32_t)(i / kTcStages) & 1u;
         mbar_wait_or_trap(&empty_bar[s], ph ^ 1u);
-        unsigned char* st = smem + (size_t)s * kTcStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], p.single ? kTcStageBytes / 2 : kTcStageBytes);
-        const int k0 = (kb_begin + i) * BK;
-        if (!p.a_mn) {
-          tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);                   // box {32 k, 128 rows}
-          if (!p.single) tma_load_2d(st + kTcTileBytes, &map_a_lo, &full_bar[s], k0, m0);
-        } else {
-          for (int j = 0; j < kTcBM / E::kMnBox; ++j) {                        // boxes {32|64 m, BK k rows}
-            tma_load_2d(st + j * E::kMnBoxBytes, &map_a_hi, &full_bar[s], m0 + E::kMnBox * j, k0);
-            if (!p.single)
-              tma_load_2d(st + kTcTileBytes + j * E::kMnBoxBytes, &map_a_lo, &full_bar[s], m0 + E::kMnBox * j, k0);
-          }
-        }
-        if (!p.b_mn) {
-          tma_load_2d(st + 2 * kTcTileBytes, &map_b_hi, &full_bar[s], k0, n0);
-          if (!p.single) tma_load_2d(st + 3 * kTcTileBytes, &map_b_lo, &full_bar[s], k0, n0);
-        } else {
-          for (int j = 0; j < kTcBN / E::kMnBox; ++j) {
-            tma_load_2d(st + 2 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_hi, &full_bar[s], n0 + E::kMnBox * j, k0);
-            if (!p.single)
-              tma_load_2d(st + 3 * kTcTileBytes + j * E::kMnBoxBytes, &map_b_lo, &full_bar[s], n0 + E::kMnBox * j, k0);
-          }
-        }
+        tc_load_stage<F16>(smem + (size_t)s * kTcStageBytes, &full_bar[s], &map_a_hi, &map_a_lo, &map_b_hi, &map_b_lo, p,
+                           cp, (kb_begin + i) * BK, m0, n0);
       }
     }
   } else if (warp == 1) {
@@ -539,7 +556,7 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             E::mma(tmem_base + (uint32_t)a * kTcBN, a_hi, b_hi, idesc, (i > c * chunk_len || ks > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
+          tc_release_stage(&empty_bar[s], cp);  // frees the stage once the MMAs above have read it
         }
         umma_commit(&acc_full[a]);
       }
@@ -617,6 +634,7 @@ tc_gemm_x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cm * p.cn > 1) tc_cluster_sync();  // no CTA leaves while a peer's commit could still arrive here
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -842,6 +860,25 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   VOCR_REQUIRE(lda % ALIGN == 0 && ldb % ALIGN == 0);
   VOCR_REQUIRE(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
                  reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15) == 0);
+  const int tiles_m = ceil_div(M, kTcBM), tiles_n = ceil_div(N, kTcBN);
+  const int tiles = tiles_n * tiles_m;
+  const int total_kb = ceil_div(K, BK);
+  const bool single = F16 && resolve_tc_products(products) == 1;
+  // split-K for long reductions that would otherwise leave most SMs idle (weight-gradient GEMMs)
+  int splits = 1;
+  if (workspace && tiles * 2 <= kNumSMs && total_kb >= 32) {
+    splits = min(min(64, (2 * kNumSMs) / tiles), total_kb / 16);
+    while (splits > 1 && sizeof(float) * (size_t)M * N * splits > workspace_bytes) --splits;
+    if (splits < 1) splits = 1;
+  }
+  int kb_per_split = ceil_div(total_kb, splits);
+  splits = ceil_div(total_kb, kb_per_split);
+  const int kind = (splits == 1 && (total_kb <= kTcPersistMaxKb || single)) ? 0 : (splits == 1 && total_kb <= 96) ? 1 : 2;
+  // Cluster shape: 2 x 2 output tiles (2 x 1 / 1 x 2 for one-tile-wide problems) for the long reductions of the weight
+  // gradients (kind 2; measured on cfg2 shapes: dW_ih 531 -> 438 us, dW_hh 161 -> 138 us).  The short-K kernels already
+  // run at ~80 % of the sustained tensor rate on their own and lose 5 - 10 % to the lock step of a cluster.
+  const bool clusters = tc_clusters_enabled() && kind == 2 && !single;
+  const int cm = (clusters && tiles_m >= 2) ? 2 : 1, cn = (clusters && tiles_n >= 2) ? 2 : 1;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   auto map2d = [](CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int bc, int br,
                   bool mn) {
@@ -849,12 +886,12 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
     return make_map_2d(m, static_cast<const float*>(base), rows, cols, ld, bc, br, mn);
   };
   bool ok = true;
-  if (!a_mn)
-    ok = ok && map2d(&ma_hi, a_hi, M, K, lda, BK, kTcBM, false) && map2d(&ma_lo, a_lo, M, K, lda, BK, kTcBM, false);
+  if (!a_mn)  // K-major: a CTA fetches 1 / cn of the tile's rows
+    ok = ok && map2d(&ma_hi, a_hi, M, K, lda, BK, kTcBM / cn, false) && map2d(&ma_lo, a_lo, M, K, lda, BK, kTcBM / cn, false);
   else
     ok = ok && map2d(&ma_hi, a_hi, K, M, lda, E::kMnBox, BK, true) && map2d(&ma_lo, a_lo, K, M, lda, E::kMnBox, BK, true);
   if (!b_mn)
-    ok = ok && map2d(&mb_hi, b_hi, N, K, ldb, BK, kTcBN, false) && map2d(&mb_lo, b_lo, N, K, ldb, BK, kTcBN, false);
+    ok = ok && map2d(&mb_hi, b_hi, N, K, ldb, BK, kTcBN / cm, false) && map2d(&mb_lo, b_lo, N, K, ldb, BK, kTcBN / cm, false);
   else
     ok = ok && map2d(&mb_hi, b_hi, K, N, ldb, E::kMnBox, BK, true) && map2d(&mb_lo, b_lo, K, N, ldb, E::kMnBox, BK, true);
   if (!ok) return VOCR_EXECUTION_FAILED;
@@ -869,27 +906,45 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
       return VOCR_EXECUTION_FAILED;
     attr_latch.set();
   }
-  const int tiles = ceil_div(N, kTcBN) * ceil_div(M, kTcBM);
-  const int total_kb = ceil_div(K, BK);
-  // split-K for long reductions that would otherwise leave most SMs idle (weight-gradient GEMMs)
-  int splits = 1;
-  if (workspace && tiles * 2 <= kNumSMs && total_kb >= 32) {
-    splits = min(min(64, (2 * kNumSMs) / tiles), total_kb / 16);
-    while (splits > 1 && sizeof(float) * (size_t)M * N * splits > workspace_bytes) --splits;
-    if (splits < 1) splits = 1;
-  }
-  int kb_per_split = ceil_div(total_kb, splits);
-  splits = ceil_div(total_kb, kb_per_split);
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
-                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, (F16 && resolve_tc_products(products) == 1) ? 1 : 0};
-  dim3 grid(ceil_div(N, kTcBN), ceil_div(M, kTcBM), splits);
-  if (splits == 1 && (total_kb <= kTcPersistMaxKb || p.single))
-    tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, p, ceil_div(N, kTcBN), tiles);
-  else if (splits == 1 && total_kb <= 96)
-    tc_gemm_x3_shortk_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  else
-    tc_gemm_x3_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, single ? 1 : 0, cm, cn};
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kTcSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err;
+  if (kind == 0) {
+    const int super_m = ceil_div(tiles_m, cm), super_n = ceil_div(tiles_n, cn), csize = cm * cn;
+    attr[0].val.clusterDim = {(unsigned)csize, 1, 1};
+    // one CTA per SM; clusters of 4 do not tile every GPC completely, so ask how many are co-resident
+    static std::atomic<int> resident[16][5];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int max_clusters = (dev >= 0 && dev < 16) ? resident[dev][csize].load(std::memory_order_relaxed) : 0;
+    if (max_clusters <= 0) {
+      cfg.gridDim = dim3((kNumSMs / csize) * csize);
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_gemm_x3_persist_kernel<F16>, &cfg) != cudaSuccess ||
+          max_clusters <= 0)
+        return VOCR_EXECUTION_FAILED;
+      max_clusters = min(max_clusters, kNumSMs / csize);
+      if (dev >= 0 && dev < 16) resident[dev][csize].store(max_clusters, std::memory_order_relaxed);
+    }
+    cfg.gridDim = dim3(min(super_m * super_n, max_clusters) * csize);
+    err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_persist_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p, super_n,
+                             super_m * super_n);
+  } else {
+    attr[0].val.clusterDim = {(unsigned)cn, (unsigned)cm, 1};
+    cfg.gridDim = dim3(ceil_div(tiles_n, cn) * cn, ceil_div(tiles_m, cm) * cm, splits);
+    if (kind == 1)
+      err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_shortk_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p);
+    else
+      err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p);
+  }
+  if (err != cudaSuccess) return VOCR_EXECUTION_FAILED;
   VOCR_CHECK_LAUNCH();
   if (splits > 1) {
     const long long total = (long long)M * N;
