@@ -908,41 +908,27 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   }
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
                  b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, single ? 1 : 0, cm, cn};
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = kTcSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t err;
-  if (kind == 0) {
-    const int super_m = ceil_div(tiles_m, cm), super_n = ceil_div(tiles_n, cn), csize = cm * cn;
-    attr[0].val.clusterDim = {(unsigned)csize, 1, 1};
-    // one CTA per SM; clusters of 4 do not tile every GPC completely, so ask how many are co-resident
-    static std::atomic<int> resident[16][5];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int max_clusters = (dev >= 0 && dev < 16) ? resident[dev][csize].load(std::memory_order_relaxed) : 0;
-    if (max_clusters <= 0) {
-      cfg.gridDim = dim3((kNumSMs / csize) * csize);
-      if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_gemm_x3_persist_kernel<F16>, &cfg) != cudaSuccess ||
-          max_clusters <= 0)
-        return VOCR_EXECUTION_FAILED;
-      max_clusters = min(max_clusters, kNumSMs / csize);
-      if (dev >= 0 && dev < 16) resident[dev][csize].store(max_clusters, std::memory_order_relaxed);
-    }
-    cfg.gridDim = dim3(min(super_m * super_n, max_clusters) * csize);
-    err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_persist_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p, super_n,
-                             super_m * super_n);
+  cudaError_t err = cudaSuccess;
+  if (kind == 0) {  // persistent, one CTA per SM
+    tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p,
+                                                                                             tiles_n, tiles);
+  } else if (cm * cn == 1) {
+    dim3 grid(tiles_n, tiles_m, splits);
+    if (kind == 1) tc_gemm_x3_shortk_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    else tc_gemm_x3_kernel<F16><<<grid, kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   } else {
+    // (a cluster launch also changes the CTA -> SM placement, so launches without a cluster keep the plain path)
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim = {(unsigned)cn, (unsigned)cm, 1};
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     cfg.gridDim = dim3(ceil_div(tiles_n, cn) * cn, ceil_div(tiles_m, cm) * cm, splits);
-    if (kind == 1)
-      err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_shortk_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p);
-    else
-      err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p);
+    err = cudaLaunchKernelEx(&cfg, tc_gemm_x3_kernel<F16>, ma_hi, ma_lo, mb_hi, mb_lo, p);
   }
   if (err != cudaSuccess) return VOCR_EXECUTION_FAILED;
   VOCR_CHECK_LAUNCH();
