@@ -245,6 +245,23 @@ int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_lo, const in
 int vocr_tc_conv3x3_wgrad_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* dz_hi,
                               const uint16_t* dz_lo, const int32_t* exp_dz, float* dw, int B, int H, int W, int Cin,
                               int Cout, void* workspace, size_t workspace_bytes, int products, vocr_stream_t stream);
+/* Inference form of one Conv + BatchNorm + ReLU unit (src/models/cnnlstm.py:263-266 with running statistics) as ONE
+ * kernel: the convolution's epilogue applies  a = relu((conv3x3(x) + bias) * scale[c] + shift[c])  (scale / shift from
+ * vocr_bn_finalize_f32 with training = 0) and writes a with strides (sB, sH, sW) - NHWC or the time-major sequence
+ * layout of the last block - and / or the FP16 pair planes of a (dense NHWC) that the next tensor-core convolution reads;
+ * either output may be NULL.  The planes are scaled by 2^e, e from the device scalar `bound` >= max |a| and stored to
+ * pair_exp[0]; vocr_bn_eval_bound_f32 derives such a bound from the weights alone (aux[0] = max_c |scale_c| (sum_k
+ * |w_ck| xbound + |bias_c|) + |shift_c|, atomicMax into aux[0], which vocr_bn_finalize_f32 zeroes; w [C][K] fp32).
+ * amax (optional device float the caller zeroes) receives the MEASURED max a: the next block's analytic bound starts from
+ * it, so the looseness of the sum-of-magnitudes bound does not compound from block to block.
+ * Replaces conv -> z, vocr_bn_relu_apply_f32(z) of the eval path: no fp32 z round trip through HBM. */
+int vocr_bn_eval_bound_f32(const float* w, const float* bias, const float* scale, const float* shift,
+                           const float* xbound, int C, int K, float* aux, vocr_stream_t stream);
+int vocr_tc_conv3x3_bnrelu_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x, const uint16_t* w_hi,
+                               const uint16_t* w_lo, const int32_t* exp_w, const float* bias, const float* scale,
+                               const float* shift, float* a, long long sB, long long sH, long long sW, uint16_t* a_hi,
+                               uint16_t* a_lo, const float* bound, int32_t* pair_exp, float* amax, int B, int H, int W,
+                               int Cin, int Cout, int products, vocr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3x3 convolutions on the tensor cores (4-D TMA implicit GEMM + tcgen05 3xTF32), same math as vocr_conv3x3_fwd_f32 /

@@ -119,6 +119,55 @@ def test_conv_bn_relu_block(cuda, B, H, W, Cin, Cout, training):
     close(ys, want, what="seq layout")
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(3, 7, 21, 64, 64), (2, 15, 50, 64, 128), (1, 7, 133, 128, 256),
+                                            (2, 3, 70, 256, 256)])
+def test_conv_bn_relu_eval_fused_epilogue(cuda, B, H, W, Cin, Cout):
+    """Inference: conv + BN(running stats) + ReLU in one kernel (vocr_tc_conv3x3_bnrelu_f16) - the fp32 activation is bit
+    for bit what conv -> z -> bn_relu_apply writes, the FP16 pair planes it emits for the next conv decode to the same
+    values to 22 bits of their (analytic, loose) bound, a two-block chain through the planes-only hand-over meets the
+    float64 reference, and so does the time-major sequence layout of the last block."""
+    from vistaocr_b200 import ops
+    g = torch.Generator().manual_seed(B * 77 + W + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3.0 * Cin ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    gamma, beta = 1 + 0.3 * torch.randn(Cout, generator=g), 0.3 * torch.randn(Cout, generator=g)
+    rm, rv = 0.1 * torch.randn(Cout, generator=g), 1 + 0.3 * torch.rand(Cout, generator=g)
+    w2 = torch.randn(64, Cout, 3, 3, generator=g) / (3.0 * Cout ** 0.5)
+    g2, b2 = 1 + 0.3 * torch.randn(64, generator=g), 0.3 * torch.randn(64, generator=g)
+    rm2, rv2 = 0.1 * torch.randn(64, generator=g), 1 + 0.3 * torch.rand(64, generator=g)
+    y1 = F.relu(F.batch_norm(F.conv2d(x.double(), w.double(), b.double(), padding=1), rm.double(), rv.double(),
+                             gamma.double(), beta.double(), False, 0.1, 1e-5))
+    y2 = F.relu(F.batch_norm(F.conv2d(y1, w2.double(), None, padding=1), rm2.double(), rv2.double(), g2.double(),
+                             b2.double(), False, 0.1, 1e-5))
+    dev = [t.to(cuda) for t in (w, b, gamma, beta, rm, rv)]
+    dev2 = [w2.to(cuda), None, g2.to(cuda), b2.to(cuda), rm2.to(cuda), rv2.to(cuda)]
+    xo = nhwc(x).to(cuda)
+    assert ops.FUSE_EVAL
+    with torch.no_grad():
+        fused = ops.conv_bn_relu(xo, *dev, False)
+        ops.FUSE_EVAL = False
+        try:
+            plain = ops.conv_bn_relu(xo, *dev, False)
+        finally:
+            ops.FUSE_EVAL = True
+        assert torch.equal(fused, plain)
+        close(nchw(fused), y1, what="fused eval block")
+        if Cout % 64 == 0:
+            hi, lo, st = fused._vocr_op.split16()
+            e = int(st[0].item())
+            dec = (hi.double() + lo.double() / 2048.0) * 2.0 ** (-e)
+            bound = float(fused._vocr_plane_bound[0].item())
+            assert bound >= fused.abs().max().item() == float(fused._vocr_bound[0].item())
+            assert (dec - fused.double()).abs().max().item() <= bound * 2.0 ** -21
+            # chain: the first block hands over planes only, the second reads them
+            a1 = ops.conv_bn_relu(xo, *dev, False, allow_planes_only=True)
+            a2 = ops.conv_bn_relu(a1, *dev2, False)
+            close(nchw(a2), y2, what="two fused blocks")
+        ys = ops.conv_bn_relu(xo, *dev, False, seq_layout=True)
+        close(ys, y1.permute(3, 0, 2, 1).reshape(W, B, H * Cout), what="fused eval block, seq layout")
+
+
 @pytest.mark.parametrize("B,H,W,Cin", [(2, 12, 38, 1), (1, 8, 22, 16), (2, 6, 9, 3)])
 def test_rapid_ds(cuda, B, H, W, Cin):
     from vistaocr_b200 import ops

@@ -278,6 +278,38 @@ extern "C" int vocr_bn_finalize_f32(const double* stats, long long count, const 
   return VOCR_OK;
 }
 
+// Upper bound of a = relu((conv(x) + bias) * scale + shift) from the weights alone:
+//   |a_c| <= |scale_c| (sum_k |w_ck| * xbound + |bias_c|) + |shift_c|,      aux[0] = max_c of that (atomicMax on the bits)
+// One warp per output channel.  Loose by the usual sum-of-magnitudes factor, which the FP16 pair format absorbs
+// (pair_f16.cuh); it lets the fused convolution epilogue emit the next layer's operand planes without seeing max |z|.
+__global__ void __launch_bounds__(256)
+bn_eval_bound_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ xbound, int C, int K,
+                     unsigned* __restrict__ aux) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += fabsf(__ldg(w + (size_t)c * K + k));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    const float zb = fmaf(s * 1.0001f, __ldg(xbound), bias ? fabsf(__ldg(bias + c)) : 0.f);  // (margin for the fp32 sum)
+    atomicMax(&aux[0], __float_as_uint(fmaf(fabsf(__ldg(scale + c)), zb, fabsf(__ldg(shift + c))) * 1.0001f));
+  }
+}
+
+// w [C][K] (K = 9 * Cin; any order inside a row), bias [C] or NULL, scale / shift [C], xbound: device scalar >= max |x|,
+// aux[0] (zeroed by vocr_bn_finalize_f32) receives the bound.
+extern "C" int vocr_bn_eval_bound_f32(const float* w, const float* bias, const float* scale, const float* shift,
+                                      const float* xbound, int C, int K, float* aux, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(w && scale && shift && xbound && aux && C > 0 && K > 0);
+  bn_eval_bound_kernel<<<ceil_div(C, 8), 256, 0, stream>>>(w, bias, scale, shift, xbound, C, K,
+                                                          reinterpret_cast<unsigned*>(aux));
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
 extern "C" int vocr_bn_relu_apply_f32(const float* z, const float* scale, const float* shift, float* a, float* a_hi,
                                       float* a_lo, int B, int H, int W, int C, long long sB, long long sH,
                                       long long sW, uint16_t* a_hi16, uint16_t* a_lo16, const float* bound,

@@ -40,7 +40,44 @@ struct TcConvParams {
   const int* exp_w;
   int single;        // 1 = hi planes only, one product per k-step (vocr_set_tc_products(1))
   unsigned* zmax;    // optional: max |z| over the whole output (atomicMax on the bit pattern of the non-negative float)
+  // Fused inference epilogue (vocr_tc_conv3x3_bnrelu_f16): a = relu(z * bn_scale[c] + bn_shift[c]) instead of z.
+  // z (may be null) then receives a with the strides below; a_hi / a_lo (may be null) receive its FP16 pair planes,
+  // dense NHWC, scaled by 2^e with e from the device bound `a_bound` (e is stored to a_exp).
+  const float* bn_scale;
+  const float* bn_shift;
+  long long sB, sH, sW;
+  __half* a_hi;
+  __half* a_lo;
+  const unsigned* a_bound;
+  int* a_exp;
 };
+
+// epilogue of one float4 group (4 consecutive output channels n..n+3 of one pixel): bias, optional BatchNorm (running
+// statistics) + ReLU, fp32 store and / or FP16 pair planes
+__device__ __forceinline__ void cv_store4(const TcConvParams& p, float (&v)[4], int n, float* zrow, size_t prow,
+                                          float psc, float& vmax) {
+  if (p.bias) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+  }
+  if (p.bn_scale) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.bn_scale + n));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.bn_shift + n));
+    v[0] = fmaxf(fmaf(v[0], sc.x, sh.x), 0.f);
+    v[1] = fmaxf(fmaf(v[1], sc.y, sh.y), 0.f);
+    v[2] = fmaxf(fmaf(v[2], sc.z, sh.z), 0.f);
+    v[3] = fmaxf(fmaf(v[3], sc.w, sh.w), 0.f);
+  }
+  // max |z|, or max a with the fused epilogue (the measured bound the NEXT layer's analytic bound starts from)
+  vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
+  if (zrow) *reinterpret_cast<float4*>(zrow + n) = make_float4(v[0], v[1], v[2], v[3]);
+  if (p.a_hi) {
+    uint2 ph, pl;
+    pair_pack4(v[0] * psc, v[1] * psc, v[2] * psc, v[3] * psc, ph, pl);
+    *reinterpret_cast<uint2*>(p.a_hi + prow + n) = ph;
+    *reinterpret_cast<uint2*>(p.a_lo + prow + n) = pl;
+  }
+}
 
 template <bool F16>
 __global__ void __launch_bounds__(kCvThreads, 1)
@@ -137,7 +174,14 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
     const int iy = r / p.BW, ix = r - iy * p.BW;
     const int y = y0 + iy, x = x0 + ix;
     const bool valid = (y < p.H) && (x < p.W);
-    float* zrow = p.z + (((size_t)b * p.H + y) * p.W + x) * p.Cout;
+    float* zrow = p.z ? p.z + (size_t)b * p.sB + (size_t)y * p.sH + (size_t)x * p.sW : nullptr;
+    const size_t prow = (((size_t)b * p.H + y) * p.W + x) * p.Cout;
+    float psc = 1.f;
+    if (p.a_hi) {
+      const int e = pair_exponent(__ldg(p.a_bound));
+      psc = exp2i(e);
+      if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) *p.a_exp = e;
+    }
     const int n_hi = min(kCvHiAcc, num_kb);
     const int out_shift = F16 ? -(__ldg(p.exp_x) + __ldg(p.exp_w)) : 0;
     float vmax = 0.f;
@@ -162,13 +206,8 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_co
         for (int j = 0; j < 32; j += 4) {
           const int n = n0 + cb + j;
           if (n < p.Cout) {  // Cout % 4 == 0
-            float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            if (p.bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            }
-            vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-            *reinterpret_cast<float4*>(zrow + n) = v;
+            float v[4] = {acc[j], acc[j + 1], acc[j + 2], acc[j + 3]};
+            cv_store4(p, v, n, zrow, prow, psc, vmax);
           }
         }
       }
@@ -297,6 +336,12 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
     const int iy = r / p.BW, ix = r - iy * p.BW;
     const int out_shift = F16 ? -(__ldg(p.exp_x) + __ldg(p.exp_w)) : 0;
     float vmax = 0.f;
+    float psc = 1.f;
+    if (p.a_hi) {
+      const int e = pair_exponent(__ldg(p.a_bound));
+      psc = exp2i(e);
+      if (blockIdx.x == 0 && threadIdx.x == 64) *p.a_exp = e;
+    }
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int set = j & 1;
@@ -308,7 +353,8 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
       const int b = pt / p.tiles_y;
       const int y = ty * p.BH + iy, x = tx * p.BW + ix;
       const bool valid = (y < p.H) && (x < p.W);
-      float* zrow = p.z + (((size_t)b * p.H + y) * p.W + x) * p.Cout;
+      float* zrow = p.z ? p.z + (size_t)b * p.sB + (size_t)y * p.sH + (size_t)x * p.sW : nullptr;
+      const size_t prow = (((size_t)b * p.H + y) * p.W + x) * p.Cout;
       mbar_wait_or_trap(&acc_full[set], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)set * 256;
@@ -330,12 +376,7 @@ tc_conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_x_hi, const _
                                                 __uint_as_float(th[q + u]));
                 v[u] = F16 ? scale_pow2(a, out_shift) : a;
               }
-              if (p.bias) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-              }
-              vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
-              *reinterpret_cast<float4*>(zrow + n) = make_float4(v[0], v[1], v[2], v[3]);
+              cv_store4(p, v, n, zrow, prow, psc, vmax);
             }
           }
         }
@@ -633,15 +674,21 @@ static void pick_tile(int H, int W, int* BW, int* BH) {
 template <bool F16>
 static int tc_conv_fwd_launch(const void* x_hi, const void* x_lo, const int* exp_x, const void* w_hi, const void* w_lo,
                               const int* exp_w, const float* bias, float* z, int B, int H, int W, int Cin, int Cout,
-                              int products, float* zmax, cudaStream_t stream) {
+                              int products, float* zmax, cudaStream_t stream, const TcConvParams* fused = nullptr) {
   constexpr int CK = TcElem<F16>::kBK;
   VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % CK == 0 && Cout % 4 == 0);
   VOCR_REQUIRE(products == 0 || products == 1 || products == 3);
   if (B == 0) return VOCR_OK;
-  VOCR_REQUIRE(x_hi && x_lo && w_hi && w_lo && z && (!F16 || (exp_x && exp_w)));
+  VOCR_REQUIRE(x_hi && x_lo && w_hi && w_lo && (z || fused) && (!F16 || (exp_x && exp_w)));
   VOCR_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo) && aligned16(z) &&
                (!bias || aligned16(bias)));
   TcConvParams p;
+  p.bn_scale = p.bn_shift = nullptr;
+  p.a_hi = p.a_lo = nullptr;
+  p.a_bound = nullptr;
+  p.a_exp = nullptr;
+  p.sB = (long long)H * W * Cout; p.sH = (long long)W * Cout; p.sW = Cout;
+  if (fused) p = *fused;  // the fused-epilogue fields; everything else is set below
   p.z = z; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.exp_x = exp_x; p.exp_w = exp_w;
   p.zmax = reinterpret_cast<unsigned*>(zmax);
@@ -701,6 +748,31 @@ extern "C" int vocr_tc_conv3x3_fwd_f16(const uint16_t* x_hi, const uint16_t* x_l
                                        int products, float* zmax, vocr_stream_t stream_) {
   return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, z, B, H, W, Cin, Cout, products, zmax,
                                   static_cast<cudaStream_t>(stream_));
+}
+
+// Inference form of one Conv + BatchNorm (running statistics) + ReLU unit (reference cnnlstm.py:263-266) in ONE kernel:
+// a = relu((conv3x3(x) + bias) * scale[c] + shift[c]), scale / shift from vocr_bn_finalize_f32(training = 0).
+// a (fp32, may be NULL) is written with strides (sB, sH, sW) (NHWC, or the time-major sequence layout of the last
+// block); a_hi / a_lo (FP16 pair planes of a, dense NHWC, may be NULL) are scaled by 2^e with e from the device scalar
+// `bound` >= max |a| (vocr_bn_eval_bound_f32), e is stored to pair_exp[0].  amax (optional device float the caller zeroes)
+// receives the measured max a.  Cin % 64 == 0, Cout % 4 == 0.
+extern "C" int vocr_tc_conv3x3_bnrelu_f16(const uint16_t* x_hi, const uint16_t* x_lo, const int32_t* exp_x,
+                                          const uint16_t* w_hi, const uint16_t* w_lo, const int32_t* exp_w,
+                                          const float* bias, const float* scale, const float* shift, float* a,
+                                          long long sB, long long sH, long long sW, uint16_t* a_hi, uint16_t* a_lo,
+                                          const float* bound, int32_t* pair_exp, float* amax, int B, int H, int W,
+                                          int Cin, int Cout, int products, vocr_stream_t stream_) {
+  VOCR_REQUIRE(scale && shift && aligned16(scale) && aligned16(shift) && (a || a_hi));
+  VOCR_REQUIRE((a_hi == nullptr) == (a_lo == nullptr) && (!a_hi || (bound && pair_exp)));
+  VOCR_REQUIRE(sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0 && (!a_hi || (aligned16(a_hi) && aligned16(a_lo))));
+  TcConvParams f;
+  f.bn_scale = scale; f.bn_shift = shift;
+  f.sB = sB; f.sH = sH; f.sW = sW;
+  f.a_hi = reinterpret_cast<__half*>(a_hi); f.a_lo = reinterpret_cast<__half*>(a_lo);
+  f.a_bound = reinterpret_cast<const unsigned*>(bound);
+  f.a_exp = pair_exp;
+  return tc_conv_fwd_launch<true>(x_hi, x_lo, exp_x, w_hi, w_lo, exp_w, bias, a, B, H, W, Cin, Cout, products, amax,
+                                  static_cast<cudaStream_t>(stream_), &f);
 }
 
 extern "C" size_t vocr_tc_conv3x3_wgrad_workspace_size(int B, int H, int W, int Cin, int Cout) {

@@ -374,6 +374,63 @@ def colstats(z, C, stats):
     check(st, "vocr_colstats_f32")
 
 
+# Inference: Conv + BatchNorm (running statistics) + ReLU as ONE kernel (vocr_tc_conv3x3_bnrelu_f16); VOCR_FUSE_EVAL=0
+# keeps the conv -> z -> bn_relu_apply sequence (same values in the fp32 activation, bit for bit).
+FUSE_EVAL = _os.environ.get("VOCR_FUSE_EVAL", "1") != "0"
+
+
+def _conv_bn_relu_eval_fused(x, weight, bias, gamma, beta, running_mean, running_var, eps, seq_layout, planes,
+                             allow_planes_only):
+    """a = relu(bn_eval(conv3x3(x) + bias)) without the fp32 z round trip: scale / shift are known before the convolution
+    runs, an upper bound of |a| follows from the weights and the bound of x (vocr_bn_eval_bound_f32), so the conv epilogue
+    writes the activation and / or the next convolution's FP16 pair planes itself."""
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    dev = x.device
+    x_op = getattr(x, "_vocr_op", None) or Operand(x, bound=getattr(x, "_vocr_bound", None))
+    xs = x_op.split16()
+    xb = getattr(x, "_vocr_bound", None)
+    if xb is None:
+        xb = x_op.bound
+    # no bound known: the split's abs-max pass left max |x| (as float bits) in state[1]
+    xb_ptr = ptr(xb) if xb is not None else _off(xs[2], 1)
+    scale = torch.empty((Cout,), dtype=F32, device=dev)
+    shift = torch.empty((Cout,), dtype=F32, device=dev)
+    aux = torch.empty((2,), dtype=F32, device=dev)  # [0] activation bound, [1] max|scale|
+    st = lib().vocr_bn_finalize_f32(None, B * H * W, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), 0.0,
+                                    float(eps), 0, ptr(scale), ptr(shift), None, None, Cout, ptr(aux), None, stream())
+    check(st, "vocr_bn_finalize_f32")
+    w = _c(weight.detach())
+    st = lib().vocr_bn_eval_bound_f32(ptr(w), ptr(bias), ptr(scale), ptr(shift), xb_ptr, Cout, 9 * Cin, ptr(aux),
+                                      stream())
+    check(st, "vocr_bn_eval_bound_f32")
+    wn = Operand(w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+    ws = wn.split16()
+    if seq_layout:
+        a = torch.empty((W, B, H * Cout), dtype=F32, device=dev)
+        strides = (H * Cout, Cout, B * H * Cout)
+    else:
+        a = torch.empty((B, H, W, Cout), dtype=F32, device=dev)  # (not written in the planes-only case)
+        strides = (H * W * Cout, W * Cout, Cout)
+    want16 = not seq_layout and Cout % 64 == 0 and planes
+    planes_only = allow_planes_only and want16 and not x.requires_grad
+    a_hi16 = torch.empty((B, H, W, Cout), dtype=torch.float16, device=dev) if want16 else None
+    a_lo16 = torch.empty((B, H, W, Cout), dtype=torch.float16, device=dev) if want16 else None
+    pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
+    amax = torch.zeros((1,), dtype=F32, device=dev)  # measured max a: where the next block's analytic bound starts
+    st = lib().vocr_tc_conv3x3_bnrelu_f16(ptr(xs[0]), ptr(xs[1]), ptr(xs[2]), ptr(ws[0]), ptr(ws[1]), ptr(ws[2]),
+                                          ptr(bias), ptr(scale), ptr(shift), None if planes_only else ptr(a),
+                                          strides[0], strides[1], strides[2], ptr(a_hi16), ptr(a_lo16),
+                                          ptr(aux) if want16 else None, ptr(pstate), ptr(amax), B, H, W, Cin, Cout,
+                                          _PRODUCTS[0], stream())
+    check(st, "vocr_tc_conv3x3_bnrelu_f16")
+    if want16:
+        a._vocr_op = Operand(None, None, (a_hi16, a_lo16, pstate))
+    a._vocr_bound = amax  # (the planes above are scaled for the analytic bound aux[0] >= amax)
+    a._vocr_plane_bound = aux
+    return a
+
+
 class _ConvBNReLU(torch.autograd.Function):
     """a = relu(batchnorm(conv3x3(x) + bias)).  x NHWC [B,H,W,Cin]; weight [Cout,Cin,3,3] (state_dict layout).
     seq_layout=True writes a as the time-major sequence [W, B, H*Cout] (feature = y*Cout + c)."""
@@ -483,6 +540,13 @@ def conv_bn_relu(x, weight, bias, gamma, beta, running_mean, running_var, traini
     when a pooling layer follows - the planes would go unread).  allow_planes_only: the caller guarantees that a
     tensor-core conv of this module is the ONLY consumer; in inference (eval statistics, no autograd) the fp32 activation
     is then not written at all - the returned tensor carries the shape and the planes, its values are undefined."""
+    Cin, Cout = x.shape[3], weight.shape[0]
+    no_grad = not torch.is_grad_enabled() or not any(
+        t is not None and t.requires_grad for t in (x, weight, bias, gamma, beta))
+    if FUSE_EVAL and USE_F16 and not training and no_grad and Cin % 64 == 0 and Cout % 4 == 0 and \
+            not _narrow(Cin, Cout) and x.is_cuda and x.dtype == F32:
+        return _conv_bn_relu_eval_fused(_c(x), weight, bias, gamma, beta, running_mean, running_var, eps, seq_layout,
+                                        planes, allow_planes_only)
     return _ConvBNReLU.apply(x, weight, bias, gamma, beta, running_mean, running_var, training, momentum, eps,
                              seq_layout, planes, allow_planes_only)
 
