@@ -60,6 +60,17 @@ int vocr_get_tc_products(void);
 int vocr_greedy_decode_f32(const float* logits, int T, int B, int A, const int32_t* lens, float thresh,
                            const int32_t* canon, int32_t* path, int32_t* labels, int32_t* counts, int ld,
                            vocr_stream_t stream);
+/* The two halves separately, for the fused inference path (the logits never reach HBM):
+ * vocr_tc_gemm_f16x3_argmax: the prob layer (src/models/cnnlstm.py:152-154; A [T*B,K] activations and W [N,K] weights as
+ *   K-major FP16 pair planes, N <= 128, K <= 1536, row m = t*B + b) with the per-frame arg-max / blank / threshold mapping
+ *   above in the GEMM epilogue: path[b*T + t] as vocr_greedy_decode_f32 writes it.  C (the logits, ldc) may be NULL.
+ * vocr_ctc_collapse_i32: path -> labels / counts (collapse repeats, drop blanks, canon as above). */
+int vocr_tc_gemm_f16x3_argmax(int M, int N, int K, const uint16_t* a_hi, const uint16_t* a_lo, int lda,
+                              const int32_t* exp_a, const uint16_t* b_hi, const uint16_t* b_lo, int ldb,
+                              const int32_t* exp_b, float* C, int ldc, const float* bias, const int32_t* lens, int T, int B,
+                              float thresh, int32_t* path, int products, vocr_stream_t stream);
+int vocr_ctc_collapse_i32(const int32_t* path, int T, int B, const int32_t* lens, const int32_t* canon, int32_t* labels,
+                          int32_t* counts, int ld, vocr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * CTC loss forward + gradient.  Replaces warpctc_pytorch.CTCLoss / warp-ctc compute_ctc_loss +

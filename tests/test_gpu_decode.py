@@ -107,3 +107,37 @@ def test_full_size_properties(cuda):
     assert torch.equal(path2, path) and torch.equal(counts2, counts)
     assert torch.equal(torch.where(valid, labels, 0), torch.where(valid, labels2, 0))
     assert rep.sum() >= 0
+
+
+@pytest.mark.parametrize("T,B,K,A", [(37, 6, 64, 5), (50, 64, 1024, 120), (33, 3, 256, 121), (9, 130, 1024, 128),
+                                     (64, 5, 512, 97), (1, 1, 8, 2)])
+def test_prob_layer_with_argmax_epilogue(cuda, T, B, K, A):
+    """The fused inference tail (ops.linear_argmax + collapse_labels: the prob-layer GEMM reduces every row to its frame
+    label in the epilogue and never writes the logits) gives exactly the path / labels / counts of the unfused sequence
+    prob layer -> logits -> vocr_greedy_decode_f32, and both match the decode oracle run on those logits."""
+    from vistaocr_b200 import ops
+    from vistaocr_b200.decoder import collapse_labels, greedy_decode_labels
+    rng = np.random.default_rng(T + 3 * B + K + A)
+    x = torch.from_numpy(rng.standard_normal((T * B, K)).astype(np.float32)).to(cuda)
+    w = torch.from_numpy((rng.standard_normal((A, K)) / K ** 0.5).astype(np.float32)).to(cuda)
+    w[min(2, A - 1)] = w[min(1, A - 1)]  # exact ties between two symbols: the lower index must win
+    b = torch.from_numpy(rng.standard_normal(A).astype(np.float32) * 0.1).to(cuda)
+    b[min(2, A - 1)] = b[min(1, A - 1)]
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    lens_dev = torch.from_numpy(lens).to(cuda)
+    assert ops.linear_argmax_supported(K, A)
+    for thresh in (-1e30, 0.3, 3 * 1 / A):
+        with torch.no_grad():
+            logits = ops.linear(x, w, b).view(T, B, A)
+            labels, counts, path = greedy_decode_labels(logits, lens_dev, thresh)
+            fpath = ops.linear_argmax(x, w, b, lens_dev, T, B, thresh)
+            flabels, fcounts = collapse_labels(fpath, lens_dev)
+        assert torch.equal(fpath, path)
+        assert torch.equal(fcounts, counts)
+        for i in range(B):
+            n = int(counts[i])
+            assert torch.equal(flabels[i, :n], labels[i, :n])
+        if thresh == 3 * 1 / A:  # the reference's threshold (decoder.py:125): the oracle's frame path
+            _, want_path = decode_labels(logits.cpu().numpy(), lens, A)
+            np.testing.assert_array_equal(fpath.cpu().numpy(), want_path)

@@ -213,7 +213,12 @@ class CnnOcrModel(nn.Module):
         if dropping and masks is None and self.num_lstm_layers > 1:
             ops.rng_advance(self._rng_state(x.device), self.num_lstm_layers - 1)
         prob = self.prob_layer[0]
-        logits = ops.linear(seq.reshape(tmax * b, 2 * hid), prob.weight, prob.bias).view(tmax, b, -1)
+        fd = getattr(self, "_fused_decode", None)  # graphs.GraphedDecoder: frame labels straight from the GEMM epilogue
+        if fd is not None and not self.training and ops.linear_argmax_supported(2 * hid, prob.weight.shape[0]):
+            fd["path"] = ops.linear_argmax(seq.reshape(tmax * b, 2 * hid), prob.weight, prob.bias, lens_dev, tmax, b,
+                                           fd["thresh"], x_bound=bound)
+            return None, lens_cpu
+        logits = ops.linear(seq.reshape(tmax * b, 2 * hid), prob.weight, prob.bias, x_bound=bound).view(tmax, b, -1)
         return logits, lens_cpu
 
     # ---- inter-layer dropout stream ---------------------------------------------------------------------------------

@@ -50,6 +50,9 @@ __device__ __forceinline__ T warp_sum(T v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// arg-max ordering of numpy / the reference decoder: NaN is maximal, otherwise plain '>' (the first maximum wins)
+__device__ __forceinline__ bool argmax_gt(float a, float b) { return (a > b) || (a != a && b == b); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

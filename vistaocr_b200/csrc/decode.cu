@@ -15,8 +15,8 @@ namespace vocr {
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
 
-// numpy ordering: NaN is maximal, otherwise plain '>'.
-__device__ __forceinline__ bool dec_gt(float a, float b) { return (a > b) || (a != a && b == b); }
+// numpy ordering: NaN is maximal, otherwise plain '>' (common.cuh).
+__device__ __forceinline__ bool dec_gt(float a, float b) { return argmax_gt(a, b); }
 
 // 8 lanes per row, 4 rows per warp pass: each lane scans A/8 elements serially, then 3 shuffle rounds finish the
 // row.  (A full-warp-per-row reduction costs 5 rounds x 2 shuffles per 480-byte row and made the kernel
@@ -186,5 +186,19 @@ extern "C" int vocr_greedy_decode_f32(const float* logits, int T, int B, int A, 
   if (launch_pdl(collapse_compact_kernel, dim3(ceil_div(B, kDecWarps)), dim3(kDecThreads), 0, stream, path, T, B, lens,
                  canon, labels, counts, ld) != cudaSuccess)
     return VOCR_EXECUTION_FAILED;
+  return VOCR_OK;
+}
+
+// Second half alone: path [B,T] (frame labels: -1 beyond the line, 0 = blank / low confidence, else the arg-max) ->
+// collapsed label strings.  For producers that already hold the frame path - the prob-layer GEMM with the arg-max in its
+// epilogue (vocr_tc_gemm_f16x3_argmax) never writes the logits.
+extern "C" int vocr_ctc_collapse_i32(const int32_t* path, int T, int B, const int32_t* lens, const int32_t* canon,
+                                     int32_t* labels, int32_t* counts, int ld, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(T >= 0 && B >= 0 && ld >= 0);
+  if (B == 0) return VOCR_OK;
+  VOCR_REQUIRE(lens && labels && counts && (T == 0 || path));
+  collapse_compact_kernel<<<ceil_div(B, kDecWarps), kDecThreads, 0, stream>>>(path, T, B, lens, canon, labels, counts, ld);
+  VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }

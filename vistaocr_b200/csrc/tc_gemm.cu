@@ -41,6 +41,12 @@ struct TcGemmParams {
   int single;        // 1 = one product per k-step on the hi planes only (reduced-precision mode: fp16 operands, fp32
                      //     accumulation; the lo planes are neither loaded nor multiplied)
   int cm, cn;        // thread-block cluster = cm x cn neighbouring output tiles (1 or 2 each); see TcClusterPos
+  // greedy-decode epilogue of the persistent kernel (vocr_tc_gemm_f16x3_argmax; N <= 128): row m = t * dec_B + b of the
+  // prob-layer output is reduced to its frame label path[b * dec_T + t] (decode.cu semantics); c may then be null
+  int32_t* path;
+  const int32_t* lens;
+  int dec_T, dec_B;
+  float thresh;
 };
 constexpr int kTcChunk = 8;  // k-blocks accumulated in TMEM before the epilogue warps drain them into fp32 registers
 
@@ -392,7 +398,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int lane_grp = warp & 3;
-    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+    const bool vec = p.c && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
     const int out_shift = F16 ? -(__ldg(p.exp_a) + __ldg(p.exp_b)) : 0;
     int j = 0;
     for (int st = cluster_id; st < num_super; st += n_clusters, ++j) {
@@ -401,8 +407,10 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
       mbar_wait_or_trap(&acc_full[set], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const int m = m0 + lane_grp * 32 + lane;
-      float* crow = p.c + (size_t)m * p.ldc;
+      float* crow = p.c ? p.c + (size_t)m * p.ldc : nullptr;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)set * 2 * kTcBN;
+      float best_v = 0.f;  // arg-max of the row (decode epilogue): columns arrive in order, the first maximum wins
+      int best_i = -1;
 #pragma unroll 1
       for (int cb = 0; cb < kTcBN; cb += 32) {
         if (n0 + cb >= p.N) break;  // warp-uniform
@@ -429,9 +437,14 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                 if (p.bias) x += __ldg(p.bias + n + q);
                 if (p.accumulate) x += crow[n + q];
                 if (p.relu) x = fmaxf(x, 0.f);
+                if (p.path && (best_i < 0 || argmax_gt(x, best_v))) {
+                  best_v = x;
+                  best_i = n + q;
+                }
               }
               v[q] = x;
             }
+            if (!crow) continue;
             if (vec && n + 3 < p.N) {
               *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -441,6 +454,12 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
             }
           }
         }
+      }
+      if (p.path && m < p.M) {  // frame label as in decode.cu: -1 beyond the line, 0 = blank or below the threshold
+        const int t = m / p.dec_B, b = m - t * p.dec_B;
+        int label = -1;
+        if (t < __ldg(p.lens + b)) label = (best_i == 0 || best_v < p.thresh) ? 0 : best_i;
+        p.path[(size_t)b * p.dec_T + t] = label;
       }
       tc_fence_before();
       mbar_arrive_cta(&acc_empty[set]);
@@ -850,13 +869,14 @@ template <bool F16>
 static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a_hi, const void* a_lo, int lda,
                           const int* exp_a, const void* b_hi, const void* b_lo, int ldb, const int* exp_b, float* C,
                           int ldc, const float* bias, int relu, int accumulate, void* workspace,
-                          size_t workspace_bytes, int products, cudaStream_t stream) {
+                          size_t workspace_bytes, int products, cudaStream_t stream,
+                          const TcGemmParams* decode = nullptr) {
   VOCR_REQUIRE(products == 0 || products == 1 || products == 3);
   using E = TcElem<F16>;
   constexpr int BK = E::kBK, ALIGN = F16 ? 8 : 4;
   VOCR_REQUIRE(M >= 0 && N >= 0 && K >= 1);
   if (M == 0 || N == 0) return VOCR_OK;
-  VOCR_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && (!F16 || (exp_a && exp_b)));
+  VOCR_REQUIRE(a_hi && a_lo && b_hi && b_lo && (C || decode) && (!F16 || (exp_a && exp_b)));
   VOCR_REQUIRE(lda % ALIGN == 0 && ldb % ALIGN == 0);
   VOCR_REQUIRE(((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(a_lo) |
                  reinterpret_cast<uintptr_t>(b_hi) | reinterpret_cast<uintptr_t>(b_lo)) & 15) == 0);
@@ -907,7 +927,11 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
     attr_latch.set();
   }
   TcGemmParams p{splits > 1 ? static_cast<float*>(workspace) : C, bias, M, N, K, ldc, relu, accumulate, a_mn ? 1 : 0,
-                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, single ? 1 : 0, cm, cn};
+                 b_mn ? 1 : 0, kb_per_split, exp_a, exp_b, single ? 1 : 0, cm, cn, nullptr, nullptr, 0, 0, 0.f};
+  if (decode) {  // arg-max epilogue: the persistent kernel with the whole row in one tile
+    VOCR_REQUIRE(kind == 0 && tiles_n == 1 && decode->path && decode->lens && (long long)decode->dec_T * decode->dec_B == M);
+    p.path = decode->path; p.lens = decode->lens; p.dec_T = decode->dec_T; p.dec_B = decode->dec_B; p.thresh = decode->thresh;
+  }
   cudaError_t err = cudaSuccess;
   if (kind == 0) {  // persistent, one CTA per SM
     tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p,
@@ -957,4 +981,20 @@ extern "C" int vocr_tc_gemm_f16x3(int a_mn, int b_mn, int M, int N, int K, const
                                   size_t workspace_bytes, int products, vocr_stream_t stream_) {
   return tc_gemm_launch<true>(a_mn, b_mn, M, N, K, a_hi, a_lo, lda, exp_a, b_hi, b_lo, ldb, exp_b, C, ldc, bias, relu,
                               accumulate, workspace, workspace_bytes, products, static_cast<cudaStream_t>(stream_));
+}
+
+// Prob layer + first half of the greedy decode in one kernel: logits[m, :] = A[m, :] . W^T + bias for row m = t * B + b
+// (A [T*B, K] activations, W [N, K], both K-major FP16 pair planes; N <= 128, K <= 1536) and, in the epilogue,
+// path[b * T + t] = the frame label of decoder.py:116-185 (arg-max with numpy's NaN ordering; 0 when the arg-max is the
+// blank or its value is below thresh; -1 for t >= lens[b]).  C may be NULL: the logits are then never written.
+extern "C" int vocr_tc_gemm_f16x3_argmax(int M, int N, int K, const uint16_t* a_hi, const uint16_t* a_lo, int lda,
+                                         const int32_t* exp_a, const uint16_t* b_hi, const uint16_t* b_lo, int ldb,
+                                         const int32_t* exp_b, float* C, int ldc, const float* bias,
+                                         const int32_t* lens, int T, int B, float thresh, int32_t* path, int products,
+                                         vocr_stream_t stream_) {
+  TcGemmParams d{};
+  d.path = path; d.lens = lens; d.dec_T = T; d.dec_B = B; d.thresh = thresh;
+  VOCR_REQUIRE(N >= 1 && N <= kTcBN && T >= 0 && B >= 0);
+  return tc_gemm_launch<true>(0, 0, M, N, K, a_hi, a_lo, lda, exp_a, b_hi, b_lo, ldb, exp_b, C, ldc, bias, 0, 0, nullptr, 0,
+                              products, static_cast<cudaStream_t>(stream_), &d);
 }

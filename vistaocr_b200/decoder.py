@@ -36,6 +36,22 @@ def greedy_decode_labels(model_output, lens, thresh, canon=None):
     return labels, counts, path[:, :T]
 
 
+def collapse_labels(path, lens, canon=None):
+    """Second half of the greedy decode on a frame path [B,T] (see ops.linear_argmax): (labels[B,T], counts[B])."""
+    _lib.require_cuda(path, "path", torch.int32)
+    B, T = path.shape
+    dev = path.device
+    lens = torch.as_tensor(lens).to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+    labels = torch.empty((B, T), dtype=torch.int32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    if canon is not None:
+        canon = torch.as_tensor(canon).to(device=dev, dtype=torch.int32).contiguous()
+    st = _lib.lib().vocr_ctc_collapse_i32(_lib.ptr(path), T, B, _lib.ptr(lens), _lib.ptr(canon), _lib.ptr(labels),
+                                          _lib.ptr(counts), T, _lib.stream())
+    _lib.check(st, "vocr_ctc_collapse_i32")
+    return labels, counts
+
+
 def _canon_map(alphabet):
     """Two alphabet indices carrying the same string collapse in the reference (it compares strings,
     decoder.py:166); returns None when all strings are distinct."""

@@ -16,7 +16,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
-from .decoder import _canon_map, greedy_decode_labels, labels_to_strings
+from .decoder import _canon_map, greedy_decode_labels, collapse_labels, labels_to_strings
 from .optim import ClampAdam, train_step
 from .warpctc import _CTC, count_infeasible
 
@@ -201,8 +201,15 @@ class GraphedDecoder:
 
         def body():
             with torch.no_grad():
-                logits, _ = model(e.x, widths_cpu)
-                labels, counts, _ = greedy_decode_labels(logits, e.lens, thresh, self._canon)
+                fd = model._fused_decode = {"thresh": thresh}
+                try:
+                    logits, _ = model(e.x, widths_cpu)
+                finally:
+                    model._fused_decode = None
+                if logits is None:  # arg-max done in the prob-layer GEMM epilogue: only the collapse is left
+                    labels, counts = collapse_labels(fd["path"], e.lens, self._canon)
+                else:
+                    labels, counts, _ = greedy_decode_labels(logits, e.lens, thresh, self._canon)
             return labels, counts
 
         model._lens_dev_override = e.lens

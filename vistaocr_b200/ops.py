@@ -214,6 +214,31 @@ def linear(x, w, b=None, relu=False, x_bound=None):
     return _Linear.apply(x, w, b, relu, x_bound)
 
 
+def linear_argmax_supported(K, N):
+    """Shapes vocr_tc_gemm_f16x3_argmax serves (one output tile per row block, the persistent short-K kernel)."""
+    return USE_F16 and N <= 128 and K % 8 == 0 and K <= 1536
+
+
+def linear_argmax(x, w, b, lens_dev, T, B, thresh, x_bound=None):
+    """Inference only: frame labels path[B,T] (int32; see vocr_greedy_decode_f32) of the logits x W^T + b, x [T*B,K] -
+    the arg-max runs in the GEMM epilogue and the logits are never written."""
+    x, w = _c(x), _c(w.detach())
+    _lib.require_cuda(x, "x", F32)
+    M, K = x.shape
+    N = w.shape[0]
+    if M != T * B or not linear_argmax_supported(K, N):
+        raise _lib.VocrError("linear_argmax: unsupported shape")
+    xs = Operand(x, bound=x_bound).split16()
+    ws = Operand(w).split16()
+    path = torch.empty((B, max(T, 1)), dtype=torch.int32, device=x.device)
+    import numpy as _np
+    st = lib().vocr_tc_gemm_f16x3_argmax(M, N, K, ptr(xs[0]), ptr(xs[1]), K, ptr(xs[2]), ptr(ws[0]), ptr(ws[1]), K,
+                                         ptr(ws[2]), None, N, ptr(b), ptr(lens_dev), T, B, float(_np.float32(thresh)),
+                                         ptr(path), _PRODUCTS[0], stream())
+    check(st, "vocr_tc_gemm_f16x3_argmax")
+    return path
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # conv3x3 + BatchNorm + ReLU block
 # ---------------------------------------------------------------------------------------------------------------
