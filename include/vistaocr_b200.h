@@ -128,6 +128,14 @@ int vocr_rds_unpool_f32(const float* dy, const float* y, const uint8_t* arg, flo
 /* first stage (Cin = 1, no data gradient): dw[16,1,3,3] and db[16] straight from the pooled gradient; ws: double[160] */
 int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const float* y, const uint8_t* arg, float* dw, float* db,
                           int B, int H, int W, double* ws, vocr_stream_t stream);
+/* 16 -> 16 channel 3x3 / pad 1 convolution of the second rapid-downsample stage (src/models/cnnlstm.py:96-121 at line height
+ * 120) and its weight / bias gradient as direct FFMA kernels: with 16 channels on both sides the implicit-GEMM kernels
+ * waste most of their tiles.  x, z, dz [B,H,W,16] NHWC; wk [144][16] = [(ky,kx,ci)][co] (the data gradient passes the
+ * flipped matrix wd of vocr_conv_weight_layout_f32); dw [16,16,3,3], db [16]; ws: float64[2320] scratch. */
+int vocr_conv3x3_c16_fwd_f32(const float* x, const float* wk, const float* bias, float* z, int B, int H, int W,
+                             vocr_stream_t stream);
+int vocr_conv3x3_c16_wgrad_f32(const float* x, const float* dz, float* dw, float* db, int B, int H, int W, double* ws,
+                               vocr_stream_t stream);
 
 /* BatchNorm2d(eps, momentum) + ReLU (src/models/cnnlstm.py:263-266).
  * vocr_bn_finalize_f32: training != 0: batch statistics from stats (see conv fwd) over `count` pixels, running

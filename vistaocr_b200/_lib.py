@@ -35,6 +35,8 @@ PROTOTYPES = {
     "vocr_rds_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
     "vocr_rds_unpool_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
     "vocr_rds_wgrad_c1_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
+    "vocr_conv3x3_c16_fwd_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
+    "vocr_conv3x3_c16_wgrad_f32": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p]),
     "vocr_bn_finalize_f32": (c_int, [c_p, c_ll, c_p, c_p, c_p, c_p, c_f, c_f, c_int, c_p, c_p, c_p, c_p, c_int, c_p,
                                      c_p, c_p]),
     "vocr_bn_relu_apply_f32": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll,
@@ -85,7 +87,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "vocr_greedy_decode_f32": 2, "vocr_ctc_loss_f32": 4, "vocr_gemm_f32": 1, "vocr_colsum_f32": 1,
     "vocr_conv_weight_layout_f32": 1, "vocr_conv3x3_fwd_f32": 1, "vocr_conv3x3_wgrad_f32": 2, "vocr_rds_fwd_f32": 1,
-    "vocr_rds_unpool_f32": 1, "vocr_rds_wgrad_c1_f32": 2, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
+    "vocr_rds_unpool_f32": 1, "vocr_rds_wgrad_c1_f32": 2, "vocr_conv3x3_c16_fwd_f32": 1, "vocr_conv3x3_c16_wgrad_f32": 2, "vocr_bn_finalize_f32": 1, "vocr_bn_relu_apply_f32": 1, "vocr_bn_relu_bwd_f32": 5,
     "vocr_fracpool_fwd_f32": 1, "vocr_fracpool_bwd_f32": 4, "vocr_bilstm_fwd_f32": 1, "vocr_bilstm_bwd_f32": 1,
     "vocr_clamp_adam_f32": 1, "vocr_dropout_f32": 1, "vocr_rng_advance": 1, "vocr_split_tf32_f32": 1, "vocr_tc_gemm_tf32x3": 1,
     "vocr_split_f16_f32": 2, "vocr_im2col3x3_f16": 2, "vocr_tc_gemm_f16x3": 1, "vocr_tc_conv3x3_fwd_f16": 1, "vocr_tc_conv3x3_wgrad_f16": 2,
@@ -106,6 +108,8 @@ WORK = {
     "vocr_tc_conv3x3_fwd": lambda a: ("flop", 2.0 * a[6] * a[7] * a[8] * 9 * a[9] * a[10]),
     "vocr_tc_conv3x3_wgrad": lambda a: ("flop", 2.0 * a[5] * a[6] * a[7] * 9 * a[8] * a[9]),
     "vocr_conv3x3_fwd_f32": lambda a: ("flop", 2.0 * a[4] * a[5] * a[6] * 9 * a[7] * a[8]),
+    "vocr_conv3x3_c16_fwd_f32": lambda a: ("flop", 2.0 * a[4] * a[5] * a[6] * 9 * 16 * 16),
+    "vocr_conv3x3_c16_wgrad_f32": lambda a: ("flop", 2.0 * a[4] * a[5] * a[6] * 9 * 16 * 16),
     "vocr_conv3x3_wgrad_f32": lambda a: ("flop", 2.0 * a[3] * a[4] * a[5] * 9 * a[6] * a[7]),
     # the recurrent step is HBM / latency bound; per (direction, step) it reads the x-projection
     # (B*4H) and writes h (B*H) - backward: reads dout, the gates, c and writes the gate gradients (B*10H) - W_hh and the

@@ -274,6 +274,38 @@ rds_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wk, const 
     for (int c = 0; c < 4; ++c) acc[p][c] = bias[cq * 4 + c];
   const int y0 = yo * 2 - 1, x0 = xo * 2 - 1;  // top-left of the 4x4 input patch
   const float* xb = x + (size_t)b * H * W * Cin;
+  if ((Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // channels four at a time: 16 float4 loads of the patch feed 576 multiply-adds (second stage, Cin = 16)
+    for (int c4 = 0; c4 < Cin; c4 += 4) {
+      float4 patch[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int yy = y0 + r, xc = x0 + c;
+          patch[r][c] = (yy >= 0 && yy < H && xc >= 0 && xc < W)
+                            ? __ldg(reinterpret_cast<const float4*>(xb + ((size_t)yy * W + xc) * Cin + c4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&s_w[((ky * 3 + kx) * Cin + c4 + cc) * kRdsCout + cq * 4]);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float4 pv = patch[(p >> 1) + ky][(p & 1) + kx];
+              const float v = cc == 0 ? pv.x : cc == 1 ? pv.y : cc == 2 ? pv.z : pv.w;
+              acc[p][0] = fmaf(v, w4.x, acc[p][0]);
+              acc[p][1] = fmaf(v, w4.y, acc[p][1]);
+              acc[p][2] = fmaf(v, w4.z, acc[p][2]);
+              acc[p][3] = fmaf(v, w4.w, acc[p][3]);
+            }
+          }
+    }
+  } else
   for (int ci = 0; ci < Cin; ++ci) {
     float patch[4][4];
 #pragma unroll
@@ -433,6 +465,168 @@ rds_wgrad_c1_kernel(const float* __restrict__ x, const float* __restrict__ dy, c
   }
 }
 
+// ---- 16 -> 16 channel 3x3 convolutions of the SECOND rapid-downsample stage (cfg3: 60 x 1000 pixels, batch 64) -------
+// With 16 channels on both sides the implicit-GEMM kernels waste 3/4 (forward / data gradient, N = 16 of a 64-wide tile)
+// to 99 % (weight gradient, a 144 x 16 output tile) of their tiles: 1.9 + 4.2 ms of a 29-ms cfg3 step.  These two direct
+// kernels are FFMA-issue bound instead (8.8 G fused multiply-adds each at that size).
+
+// z[p][co] = sum_{tap,ci} x[p + tap][ci] wk[(tap, ci)][co] (+ bias).  One thread = 4 consecutive pixels of a row x 4
+// output channels: per (ky, input-channel quad) it loads 6 float4 of x and reads 12 float4 of weights from shared memory
+// for 192 multiply-adds.
+__global__ void __launch_bounds__(256)
+conv16_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
+                  float* __restrict__ z, int H, int W) {
+  __shared__ float4 s_w[144 * 4];  // [(tap, ci)][co quad]
+  for (int i = threadIdx.x; i < 144 * 4; i += 256) s_w[i] = __ldg(reinterpret_cast<const float4*>(wk) + i);
+  __syncthreads();
+  const int cq = threadIdx.x & 3, pg = threadIdx.x >> 2;
+  const int x0 = blockIdx.x * 256 + pg * 4, y = blockIdx.y, b = blockIdx.z;
+  if (x0 >= W) return;
+  float acc[4][4];
+  const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    acc[p][0] = bv.x; acc[p][1] = bv.y; acc[p][2] = bv.z; acc[p][3] = bv.w;
+  }
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    const float4* row = reinterpret_cast<const float4*>(x + ((size_t)b * H + yy) * W * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // input channels 4q .. 4q+3
+      float4 xv[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int xc = x0 - 1 + j;
+        xv[j] = (xc >= 0 && xc < W) ? __ldg(row + (size_t)xc * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 w4 = s_w[((ky * 3 + kx) * 16 + q * 4 + c) * 4 + cq];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float4 xx = xv[p + kx];
+            const float v = c == 0 ? xx.x : c == 1 ? xx.y : c == 2 ? xx.z : xx.w;
+            acc[p][0] = fmaf(v, w4.x, acc[p][0]);
+            acc[p][1] = fmaf(v, w4.y, acc[p][1]);
+            acc[p][2] = fmaf(v, w4.z, acc[p][2]);
+            acc[p][3] = fmaf(v, w4.w, acc[p][3]);
+          }
+        }
+      }
+    }
+  }
+  float4* zrow = reinterpret_cast<float4*>(z + (((size_t)b * H + y) * W) * 16);
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    if (x0 + p < W) zrow[(size_t)(x0 + p) * 4 + cq] = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+}
+
+// dw[co][ci][tap] = sum_p x[p + tap][ci] dz[p][co],  db[co] = sum_p dz[p][co]  -> float64 out[2304 + 16] (atomics).
+// A CTA walks over (image, 64-pixel column chunk) items and, inside one, over the rows; per row it stages the three x rows
+// (with halo) and the dz row in shared memory.  256 threads = 4 pixel groups x (16 ci x 4 co quads): a thread keeps
+// 9 taps x 4 output channels in registers and slides a 3-wide window of x along its 16 pixels - per pixel 3 + 1
+// shared-memory loads for 36 multiply-adds.
+constexpr int kW16Chunk = 64;
+__global__ void __launch_bounds__(256)
+conv16_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, int B, int H, int W, int n_items,
+                    int chunks, double* __restrict__ out) {
+  __shared__ __align__(16) float xs[3][kW16Chunk + 2][16];
+  __shared__ __align__(16) float ds[kW16Chunk][16];
+  __shared__ float red[64][37];
+  const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
+  const int ci = t & 15, coq = t >> 4;
+  float acc[9][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / chunks, xc0 = (item - b * chunks) * kW16Chunk;
+    for (int y = 0; y < H; ++y) {
+      __syncthreads();  // the previous row's tiles are consumed
+      // stage: 3 rows x 66 pixels x 4 float4 of x, 64 pixels x 4 float4 of dz
+      for (int i = tid; i < 3 * (kW16Chunk + 2) * 4; i += 256) {
+        const int r = i / ((kW16Chunk + 2) * 4), rem = i - r * (kW16Chunk + 2) * 4;
+        const int c = rem >> 2, q = rem & 3;
+        const int yy = y + r - 1, xx = xc0 - 1 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + yy) * W + xx) * 16) + q);
+        *reinterpret_cast<float4*>(&xs[r][c][q * 4]) = v;
+      }
+      for (int i = tid; i < kW16Chunk * 4; i += 256) {
+        const int c = i >> 2, q = i & 3;
+        const int xx = xc0 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xx < W) v = __ldg(reinterpret_cast<const float4*>(dz + (((size_t)b * H + y) * W + xx) * 16) + q);
+        *reinterpret_cast<float4*>(&ds[c][q * 4]) = v;
+      }
+      __syncthreads();
+      const int p0 = g * 16;
+      float w0[3], w1[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        w0[r] = xs[r][p0][ci];
+        w1[r] = xs[r][p0 + 1][ci];
+      }
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const float4 d = *reinterpret_cast<const float4*>(&ds[p0 + p][coq * 4]);
+        if (ci == 0) {
+          accb[0] += d.x; accb[1] += d.y; accb[2] += d.z; accb[3] += d.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float w2 = xs[r][p0 + p + 2][ci];
+          acc[r * 3 + 0][0] = fmaf(w0[r], d.x, acc[r * 3 + 0][0]);
+          acc[r * 3 + 0][1] = fmaf(w0[r], d.y, acc[r * 3 + 0][1]);
+          acc[r * 3 + 0][2] = fmaf(w0[r], d.z, acc[r * 3 + 0][2]);
+          acc[r * 3 + 0][3] = fmaf(w0[r], d.w, acc[r * 3 + 0][3]);
+          acc[r * 3 + 1][0] = fmaf(w1[r], d.x, acc[r * 3 + 1][0]);
+          acc[r * 3 + 1][1] = fmaf(w1[r], d.y, acc[r * 3 + 1][1]);
+          acc[r * 3 + 1][2] = fmaf(w1[r], d.z, acc[r * 3 + 1][2]);
+          acc[r * 3 + 1][3] = fmaf(w1[r], d.w, acc[r * 3 + 1][3]);
+          acc[r * 3 + 2][0] = fmaf(w2, d.x, acc[r * 3 + 2][0]);
+          acc[r * 3 + 2][1] = fmaf(w2, d.y, acc[r * 3 + 2][1]);
+          acc[r * 3 + 2][2] = fmaf(w2, d.z, acc[r * 3 + 2][2]);
+          acc[r * 3 + 2][3] = fmaf(w2, d.w, acc[r * 3 + 2][3]);
+          w0[r] = w1[r];
+          w1[r] = w2;
+        }
+      }
+    }
+  }
+  // the four pixel groups add their partials in turn (fixed order), then one float64 atomic per output and CTA
+  for (int gg = 0; gg < 4; ++gg) {
+    __syncthreads();
+    if (g == gg) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* r = &red[t][k * 4 + c];
+          *r = (gg == 0 ? 0.f : *r) + acc[k][c];
+        }
+      if (ci == 0) {  // bias partials: 16 values per group, straight out
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(&out[2304 + coq * 4 + c], (double)accb[c]);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        atomicAdd(&out[((coq * 4 + c) * 16 + ci) * 9 + k], (double)red[t][k * 4 + c]);
+  }
+}
+
 __global__ void f64_to_f32_conv_kernel(const double* __restrict__ in, float* __restrict__ a, int na,
                                        float* __restrict__ b, int nb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -557,6 +751,41 @@ extern "C" int vocr_rds_wgrad_c1_f32(const float* x, const float* dy, const floa
     VOCR_CHECK_LAUNCH();
   }
   f64_to_f32_conv_kernel<<<1, 192, 0, stream>>>(ws, dw, 144, db, 16);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// 3x3 / pad 1 convolution with 16 input and 16 output channels (second rapid-downsample stage: its data gradient runs
+// through here with the flipped weight matrix wd of vocr_conv_weight_layout_f32).  wk [144][16], bias [16] or NULL.
+extern "C" int vocr_conv3x3_c16_fwd_f32(const float* x, const float* wk, const float* bias, float* z, int B, int H,
+                                        int W, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && B <= 65535 && H <= 65535);
+  if (B == 0) return VOCR_OK;
+  VOCR_REQUIRE(x && wk && z && aligned16(x) && aligned16(wk) && aligned16(z) && (!bias || aligned16(bias)));
+  dim3 grid(ceil_div(W, 256), H, B);
+  conv16_fwd_kernel<<<grid, 256, 0, stream>>>(x, wk, bias, z, H, W);
+  VOCR_CHECK_LAUNCH();
+  return VOCR_OK;
+}
+
+// Weight / bias gradient of that convolution: dw[16,16,3,3] (state_dict layout), db[16] from x and dz (both
+// [B,H,W,16]).  ws: float64[2320] scratch.
+extern "C" int vocr_conv3x3_c16_wgrad_f32(const float* x, const float* dz, float* dw, float* db, int B, int H, int W,
+                                          double* ws, vocr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VOCR_REQUIRE(B >= 0 && H > 0 && W > 0 && dw && db && ws);
+  if (cudaMemsetAsync(ws, 0, sizeof(double) * 2320, stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
+  const int chunks = ceil_div(W, kW16Chunk);
+  const long long items = (long long)B * chunks;
+  VOCR_REQUIRE(items < (1ll << 31));
+  if (items > 0) {
+    VOCR_REQUIRE(x && dz && aligned16(x) && aligned16(dz));
+    const int grid = (int)min((long long)kNumSMs * 4, items);
+    conv16_wgrad_kernel<<<grid, 256, 0, stream>>>(x, dz, B, H, W, (int)items, chunks, ws);
+    VOCR_CHECK_LAUNCH();
+  }
+  f64_to_f32_conv_kernel<<<ceil_div(2320, 256), 256, 0, stream>>>(ws, dw, 2304, db, 16);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }

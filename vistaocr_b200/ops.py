@@ -196,13 +196,31 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         xo, wo = ctx.ops
         ctx.ops = None
-        dyo = Operand(dy)
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            mm(0, 0, M, K, N, dyo, N, wo, K, dx, K)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            mm(1, 0, N, K, M, dyo, N, xo, K, dw, K)
+        if USE_F16 and N % 8 != 0 and K % 8 == 0 and M > 0:
+            # an output width that is not a multiple of 8 (alphabet 166 of cfg3) would send both backward GEMMs to the
+            # FFMA engine (dy is their reduction- / row-major operand with leading dimension N): pad dy and W with zero
+            # columns / rows to the next multiple of 8 instead - two small copies
+            Np = (N + 7) // 8 * 8
+            dyp = torch.zeros((M, Np), dtype=F32, device=dy.device)
+            dyp[:, :N].copy_(dy)
+            dyo = Operand(dyp)
+            if ctx.needs_input_grad[0]:
+                wp = torch.zeros((Np, K), dtype=F32, device=dy.device)
+                wp[:N].copy_(w)
+                dx = torch.empty_like(x)
+                mm(0, 0, M, K, Np, dyo, Np, Operand(wp), K, dx, K)
+            if ctx.needs_input_grad[1]:
+                dwp = torch.empty((Np, K), dtype=F32, device=dy.device)
+                mm(1, 0, Np, K, M, dyo, Np, xo, K, dwp, K)
+                dw = dwp[:N]
+        else:
+            dyo = Operand(dy)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                mm(0, 0, M, K, N, dyo, N, wo, K, dx, K)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty_like(w)
+                mm(1, 0, N, K, M, dyo, N, xo, K, dw, K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((N,), dtype=F32, device=x.device)
             colsum(dy, M, N, N, db)
@@ -612,6 +630,19 @@ class _RapidDS(torch.autograd.Function):
         dpre = torch.empty((B, H, W, 16), dtype=F32, device=dev)
         st = lib().vocr_rds_unpool_f32(ptr(dy), ptr(y), ptr(arg), ptr(dpre), B, H, W, stream())
         check(st, "vocr_rds_unpool_f32")
+        if Cin == 16:  # second stage (line height 120): direct 16 -> 16 kernels
+            dx = None
+            if ctx.needs_input_grad[0]:
+                _, wd = _weight_layout(_c(weight), False, True)
+                dx = torch.empty((B, H, W, 16), dtype=F32, device=dev)
+                st = lib().vocr_conv3x3_c16_fwd_f32(ptr(dpre), ptr(wd), None, ptr(dx), B, H, W, stream())
+                check(st, "vocr_conv3x3_c16_fwd_f32")
+            dw = torch.empty((16, 16, 3, 3), dtype=F32, device=dev)
+            db = torch.empty((16,), dtype=F32, device=dev)
+            ws = torch.empty((2320,), dtype=torch.float64, device=dev)
+            st = lib().vocr_conv3x3_c16_wgrad_f32(ptr(x), ptr(dpre), ptr(dw), ptr(db), B, H, W, ptr(ws), stream())
+            check(st, "vocr_conv3x3_c16_wgrad_f32")
+            return dx, dw, db
         dx = None
         if ctx.needs_input_grad[0]:
             _, wd = _weight_layout(_c(weight), False, True)
