@@ -361,6 +361,8 @@ def run_train(ctx, name):
     def step_fn(batches, read_loss, eager=False):
         def fn(i):
             b = batches[i % len(batches)]
+            if read_loss and use_graphs and not eager:  # e2e: the next batch's H2D copy runs under this step's kernels
+                graphed.prefetch(batches[(i + 1) % len(batches)])
             loss = train_step(b, model, criterion, optimizer) if (eager or not use_graphs) else graphed(b)
             if read_loss:
                 float(loss[0].item())  # D2H read of the step's result
@@ -493,21 +495,25 @@ def run_decode(ctx, name):
     steps = args.steps if name == "decode_cfg1" else len(host)
     pinned = [(x.pin_memory(), w) for x, w in host]
     resident = [(x.to(dev), w) for x, w in host]
-    graphed = GraphedDecoder(model, capture_after=1, max_graphs=4)
-    use_graphs = (not args.eager) and name == "decode_cfg1"  # cfg5 geometries do not repeat: eager
+    # cfg5 geometries do not repeat: its GraphedDecoder never captures and runs its (fused) eager path
+    use_graphs = (not args.eager) and name == "decode_cfg1"
+    graphed = GraphedDecoder(model, capture_after=1 if use_graphs else 1 << 30, max_graphs=4)
+    uncaptured = GraphedDecoder(model, capture_after=1 << 30)  # the same call sequence, launched kernel by kernel
     thresh = 3 * 1 / len(model.alphabet)
 
     def device_fn(i):  # resident inputs, result stays on the device
         x, w = resident[i % len(resident)]
-        if use_graphs and graphed.labels(x, w) is not None:
+        if not args.eager:
+            (graphed if use_graphs else uncaptured).labels(x, w, allow_eager=True)
             return
         with torch.no_grad():
             logits, lens = model(x, w)
             greedy_decode_labels(logits, lens, thresh)
 
-    def e2e_fn(i):  # pinned host batch in, strings out
+    def e2e_fn(i):  # pinned host batch in, strings out; the next batch's H2D copy runs under this batch's kernels
         x, w = pinned[i % len(pinned)]
-        if use_graphs:
+        if not args.eager:
+            graphed.prefetch(pinned[(i + 1) % len(pinned)][0])
             graphed(x, w, uxxxx=True)
         else:
             with torch.no_grad():

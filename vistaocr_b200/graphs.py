@@ -30,6 +30,37 @@ class _Entry:
     pass
 
 
+class _Prefetcher:
+    """Host -> device copy of the NEXT batch's images on a side stream while the current step runs (what a DataLoader's
+    pinned-memory prefetch does for the reference loop): `prefetch(x)` starts the copy, `take(x)` returns the device copy
+    (the current stream waits for it) when x is the tensor that was prefetched, else x itself."""
+
+    def __init__(self):
+        self.stream = None
+        self.item = None
+
+    def prefetch(self, x, device):
+        if not torch.is_tensor(x) or x.is_cuda:
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(self.stream):
+            xd = x.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.item = (x, xd, ev)
+
+    def take(self, x):
+        it = self.item
+        if it is None or it[0] is not x:
+            return x
+        self.item = None
+        cur = torch.cuda.current_stream()
+        cur.wait_event(it[2])
+        it[1].record_stream(cur)
+        return it[1]
+
+
 class _GraphCache:
     def __init__(self, capture_after, max_graphs):
         self.capture_after, self.max_graphs = capture_after, max_graphs
@@ -67,6 +98,11 @@ class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, capture_after=1, max_graphs=8):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.graphs = _GraphCache(capture_after, max_graphs)
+        self._pf = _Prefetcher()
+
+    def prefetch(self, batch):
+        """Optional: start the host -> device copy of the images of the batch that will be passed to the NEXT call."""
+        self._pf.prefetch(batch[0], next(self.model.parameters()).device)
 
     def _eligible(self):
         c = self.criterion
@@ -75,6 +111,9 @@ class GraphedTrainStep:
 
     def __call__(self, batch):
         x, target, widths, target_widths, _ = batch
+        xd = self._pf.take(x)
+        if xd is not x:
+            x, batch = xd, (xd,) + tuple(batch[1:])
         if not self._eligible():
             self.graphs.eager_calls += 1
             return train_step(batch, self.model, self.criterion, self.optimizer)
@@ -151,19 +190,43 @@ class GraphedDecoder:
         self.model = model
         self.graphs = _GraphCache(capture_after, max_graphs)
         self._canon = "unset"
+        self._pf = _Prefetcher()
 
-    def _eager(self, x, widths, uxxxx):
-        self.graphs.eager_calls += 1
+    def prefetch(self, x):
+        """Optional: start the host -> device copy of the images that will be passed to the NEXT call."""
+        self._pf.prefetch(x, next(self.model.parameters()).device)
+
+    def _canon_dev(self, dev):
+        if self._canon == "unset":
+            c = _canon_map(self.model.alphabet)
+            self._canon = None if c is None else torch.from_numpy(c).to(dev)
+        return self._canon
+
+    def _forward_labels(self, x_dev, widths_cpu, lens_dev):
+        """Eval forward + greedy decode on the device: (labels, counts).  The frame labels come straight from the
+        prob-layer GEMM's epilogue when the shapes allow it (the logits are then never written)."""
+        model = self.model
+        thresh = 3 * 1 / len(model.alphabet)
+        canon = self._canon_dev(x_dev.device)
         with torch.no_grad():
-            logits, lens = self.model(x.cuda(non_blocking=True), widths)
-        return self.model.decode_without_lm(logits, lens, uxxxx=uxxxx)
+            fd = model._fused_decode = {"thresh": thresh}
+            try:
+                logits, _ = model(x_dev, widths_cpu)
+            finally:
+                model._fused_decode = None
+            if logits is None:  # arg-max done in the GEMM epilogue: only the collapse is left
+                return collapse_labels(fd["path"], lens_dev, canon)
+            labels, counts, _ = greedy_decode_labels(logits, lens_dev, thresh, canon)
+            return labels, counts
 
-    def labels(self, x, widths):
-        """Device result of one batch: (labels[B,T] int32, counts[B] int32) - static buffers of the graph, valid until
-        the next call with the same geometry; None when the batch ran eagerly."""
+    def labels(self, x, widths, allow_eager=False):
+        """Device result of one batch: (labels[B,T] int32, counts[B] int32).  Replayed geometries return the graph's
+        static buffers (valid until the next call with the same geometry); a geometry that is not captured (yet) runs
+        eagerly when allow_eager is set, else None is returned."""
         model = self.model
         if model.training:
             return None
+        x = self._pf.take(x)
         wl = widths.tolist() if torch.is_tensor(widths) else list(widths)
         lens = _lens_for(model, wl)
         if any(lens[i] < lens[i + 1] for i in range(len(lens) - 1)):
@@ -171,7 +234,16 @@ class GraphedDecoder:
         key = (tuple(x.shape), max(lens), ops.get_precision())
         e, want_capture = self.graphs.lookup(key)
         if e is None and not want_capture:
-            return None
+            if not allow_eager:
+                return None
+            self.graphs.eager_calls += 1
+            dev = next(model.parameters()).device
+            lens_dev = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+            model._lens_dev_override = lens_dev
+            try:
+                return self._forward_labels(x.to(dev, non_blocking=True), torch.tensor(wl, dtype=torch.int32), lens_dev)
+            finally:
+                model._lens_dev_override = None
         if e is None:
             e = self._capture(key, x, wl)
         e.x.copy_(x, non_blocking=True)
@@ -181,36 +253,27 @@ class GraphedDecoder:
         return e.labels, e.counts
 
     def __call__(self, x, widths, uxxxx=False):
-        out = self.labels(x, widths)
-        if out is None:
-            return self._eager(x, widths, uxxxx)
+        x = self._pf.take(x)
+        if self.model.training:
+            self.graphs.eager_calls += 1
+            with torch.no_grad():
+                logits, lens = self.model(x.cuda(non_blocking=True), widths)
+            return self.model.decode_without_lm(logits, lens, uxxxx=uxxxx)
+        out = self.labels(x, widths, allow_eager=True)
         return labels_to_strings(out[0], out[1], self.model.alphabet, uxxxx)
 
     def _capture(self, key, x, widths):
         model = self.model
         dev = next(model.parameters()).device
-        if self._canon == "unset":
-            c = _canon_map(model.alphabet)
-            self._canon = None if c is None else torch.from_numpy(c).to(dev)
+        self._canon_dev(dev)
         e = _Entry()
         e.x = torch.zeros(tuple(x.shape), dtype=torch.float32, device=dev)
         e.lens = torch.zeros((x.shape[0],), dtype=torch.int32, device=dev)
         ops.const_scalar(dev, 1.0)
         widths_cpu = torch.tensor(widths, dtype=torch.int32)
-        thresh = 3 * 1 / len(model.alphabet)
 
         def body():
-            with torch.no_grad():
-                fd = model._fused_decode = {"thresh": thresh}
-                try:
-                    logits, _ = model(e.x, widths_cpu)
-                finally:
-                    model._fused_decode = None
-                if logits is None:  # arg-max done in the prob-layer GEMM epilogue: only the collapse is left
-                    labels, counts = collapse_labels(fd["path"], e.lens, self._canon)
-                else:
-                    labels, counts, _ = greedy_decode_labels(logits, e.lens, thresh, self._canon)
-            return labels, counts
+            return self._forward_labels(e.x, widths_cpu, e.lens)
 
         model._lens_dev_override = e.lens
         try:
