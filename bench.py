@@ -361,8 +361,6 @@ def run_train(ctx, name):
     def step_fn(batches, read_loss, eager=False):
         def fn(i):
             b = batches[i % len(batches)]
-            if read_loss and use_graphs and not eager:  # e2e: the next batch's H2D copy runs under this step's kernels
-                graphed.prefetch(batches[(i + 1) % len(batches)])
             loss = train_step(b, model, criterion, optimizer) if (eager or not use_graphs) else graphed(b)
             if read_loss:
                 float(loss[0].item())  # D2H read of the step's result
@@ -510,10 +508,9 @@ def run_decode(ctx, name):
             logits, lens = model(x, w)
             greedy_decode_labels(logits, lens, thresh)
 
-    def e2e_fn(i):  # pinned host batch in, strings out; the next batch's H2D copy runs under this batch's kernels
+    def e2e_fn(i):  # pinned host batch in, strings out
         x, w = pinned[i % len(pinned)]
         if not args.eager:
-            graphed.prefetch(pinned[(i + 1) % len(pinned)][0])
             graphed(x, w, uxxxx=True)
         else:
             with torch.no_grad():

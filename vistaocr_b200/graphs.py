@@ -30,37 +30,6 @@ class _Entry:
     pass
 
 
-class _Prefetcher:
-    """Host -> device copy of the NEXT batch's images on a side stream while the current step runs (what a DataLoader's
-    pinned-memory prefetch does for the reference loop): `prefetch(x)` starts the copy, `take(x)` returns the device copy
-    (the current stream waits for it) when x is the tensor that was prefetched, else x itself."""
-
-    def __init__(self):
-        self.stream = None
-        self.item = None
-
-    def prefetch(self, x, device):
-        if not torch.is_tensor(x) or x.is_cuda:
-            return
-        if self.stream is None:
-            self.stream = torch.cuda.Stream(device=device)
-        with torch.cuda.stream(self.stream):
-            xd = x.to(device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self.item = (x, xd, ev)
-
-    def take(self, x):
-        it = self.item
-        if it is None or it[0] is not x:
-            return x
-        self.item = None
-        cur = torch.cuda.current_stream()
-        cur.wait_event(it[2])
-        it[1].record_stream(cur)
-        return it[1]
-
-
 class _GraphCache:
     def __init__(self, capture_after, max_graphs):
         self.capture_after, self.max_graphs = capture_after, max_graphs
@@ -98,11 +67,6 @@ class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, capture_after=1, max_graphs=8):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.graphs = _GraphCache(capture_after, max_graphs)
-        self._pf = _Prefetcher()
-
-    def prefetch(self, batch):
-        """Optional: start the host -> device copy of the images of the batch that will be passed to the NEXT call."""
-        self._pf.prefetch(batch[0], next(self.model.parameters()).device)
 
     def _eligible(self):
         c = self.criterion
@@ -111,9 +75,6 @@ class GraphedTrainStep:
 
     def __call__(self, batch):
         x, target, widths, target_widths, _ = batch
-        xd = self._pf.take(x)
-        if xd is not x:
-            x, batch = xd, (xd,) + tuple(batch[1:])
         if not self._eligible():
             self.graphs.eager_calls += 1
             return train_step(batch, self.model, self.criterion, self.optimizer)
@@ -190,11 +151,6 @@ class GraphedDecoder:
         self.model = model
         self.graphs = _GraphCache(capture_after, max_graphs)
         self._canon = "unset"
-        self._pf = _Prefetcher()
-
-    def prefetch(self, x):
-        """Optional: start the host -> device copy of the images that will be passed to the NEXT call."""
-        self._pf.prefetch(x, next(self.model.parameters()).device)
 
     def _canon_dev(self, dev):
         if self._canon == "unset":
@@ -226,7 +182,6 @@ class GraphedDecoder:
         model = self.model
         if model.training:
             return None
-        x = self._pf.take(x)
         wl = widths.tolist() if torch.is_tensor(widths) else list(widths)
         lens = _lens_for(model, wl)
         if any(lens[i] < lens[i + 1] for i in range(len(lens) - 1)):
@@ -253,12 +208,11 @@ class GraphedDecoder:
         return e.labels, e.counts
 
     def __call__(self, x, widths, uxxxx=False):
-        x = self._pf.take(x)
         if self.model.training:
             self.graphs.eager_calls += 1
             with torch.no_grad():
                 logits, lens = self.model(x.cuda(non_blocking=True), widths)
-            return self.model.decode_without_lm(logits, lens, uxxxx=uxxxx)
+                return self.model.decode_without_lm(logits, lens, uxxxx=uxxxx)
         out = self.labels(x, widths, allow_eager=True)
         return labels_to_strings(out[0], out[1], self.model.alphabet, uxxxx)
 
