@@ -290,7 +290,10 @@ NOTES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/ (cfg2 shapes);
 # kernels launched with several shapes per step have no single figure
-NCU_TRAFFIC = {"vocr_bilstm_bwd_f32": 294.9e6 + 171.4e6, "vocr_bilstm_fwd_f32": 199.4e6 + 247.1e6}
+NCU_TRAFFIC = {"vocr_bilstm_bwd_f32": 294.9e6 + 171.4e6, "vocr_bilstm_fwd_f32": 199.4e6 + 247.1e6,
+               # several shapes per step: MEAN over the launches of a cfg2 step (profiles/r02_launches.md)
+               "vocr_tc_conv3x3_fwd_f16": 342e6, "vocr_tc_gemm_f16x3": 304e6, "vocr_tc_conv3x3_wgrad_f16": 385e6,
+               "vocr_split_f16_f32": 82e6, "vocr_bn_relu_bwd_f32": 1146e6}
 
 
 def rooflines_from(prof, pk, top=6):
