@@ -26,6 +26,10 @@ constexpr int kTcThreads = 192;
 constexpr int kTcTileBytes = kTcBM * kTcBK * 4;         // 16 KB
 constexpr int kTcStageBytes = 4 * kTcTileBytes;         // A_hi, A_lo, B_hi, B_lo
 constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+// persistent kernel: 8 epilogue warps (two per TMEM quadrant, 64 columns each) + a 32 x 32 fp32 transposition buffer per
+// epilogue warp (16-byte chunks XOR-swizzled by the row), see its epilogue
+constexpr int kTcPersistThreads = 64 + 8 * 32;
+constexpr int kTcPersistSmemBytes = kTcSmemBytes + 8 * 32 * 32 * 4;
 constexpr uint32_t kTmemCols = 512;  // 3 rotating hi*hi accumulators + 1 for the lo products, 128 columns each
 constexpr int kTcHiAcc = 3;
 
@@ -301,7 +305,7 @@ tc_gemm_x3_shortk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 constexpr int kTcPersistMaxKb = 24;
 
 template <bool F16>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcPersistThreads, 1)
 tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                           TcGemmParams p, int super_n, int num_super) {
@@ -330,7 +334,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 128);
+      mbar_init(&acc_empty[a], kTcPersistThreads - 64);
     }
     mbar_fence_init();
   }
@@ -396,10 +400,15 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
-    const int lane_grp = warp & 3;
+    // ================================ epilogue (warps 2..9) ================================
+    // warp w reads TMEM lanes [32 (w % 4), +32) - two warps per quadrant, each draining half of the tile's columns
+    const int lane_grp = warp & 3, chalf = (warp - 2) >> 2;
     const bool vec = p.c && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
     const int out_shift = F16 ? -(__ldg(p.exp_a) + __ldg(p.exp_b)) : 0;
+    // wide outputs go through the per-warp transposition buffer (behind the barriers, 16-B aligned)
+    float* stg = reinterpret_cast<float*>(smem + kTcStages * kTcStageBytes + 256) + (warp - 2) * 32 * 32;
+    const bool coalesce = vec && !p.accumulate && !p.path && p.N >= 256 && (p.N & 3) == 0 &&
+                          (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int j = 0;
     for (int st = cluster_id; st < num_super; st += n_clusters, ++j) {
       const int set = j & 1;
@@ -411,12 +420,15 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
       const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)set * 2 * kTcBN;
       float best_v = 0.f;  // arg-max of the row (decode epilogue): columns arrive in order, the first maximum wins
       int best_i = -1;
+      // (arg-max epilogue: a row must stay in one thread - the first warp of the quadrant takes all columns)
+      const int cb0 = p.path ? 0 : chalf * (kTcBN / 2), cb1 = p.path ? (chalf == 0 ? kTcBN : 0) : (chalf + 1) * (kTcBN / 2);
 #pragma unroll 1
-      for (int cb = 0; cb < kTcBN; cb += 32) {
+      for (int cb = cb0; cb < cb1; cb += 32) {
         if (n0 + cb >= p.N) break;  // warp-uniform
         uint32_t th[32], tl[32];
-        tmem_ld32(lane_addr + (uint32_t)cb, th);
-        tmem_ld32(lane_addr + (uint32_t)(kTcBN + cb), tl);
+        tmem_ld32_nowait(lane_addr + (uint32_t)cb, th);
+        tmem_ld32_nowait(lane_addr + (uint32_t)(kTcBN + cb), tl);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float r[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -424,7 +436,34 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                                    : fmaf(__uint_as_float(tl[q]), F16 ? 1.f / kPairLoScale : 1.f, __uint_as_float(th[q]));
           r[q] = F16 ? scale_pow2(v, out_shift) : v;
         }
-        if (m < p.M) {
+        if (coalesce) {
+          // An epilogue thread owns a ROW of the tile: storing it directly makes every warp store touch 32 rows x 16 B
+          // (half-filled sectors, 16 KB apart at N = 4096) - measured 0.6 TB/s, which bounds the K = 128 projection
+          // outright (1.22 ms for an 814-MB output).  Transpose the 32 x 32 block through shared memory instead so that
+          // a store instruction writes four full 128-byte lines.
+#pragma unroll
+          for (int q0 = 0; q0 < 32; q0 += 4) {
+            const int n = n0 + cb + q0;
+            float4 v = make_float4(r[q0], r[q0 + 1], r[q0 + 2], r[q0 + 3]);
+            if (p.bias && n + 3 < p.N) {  // (N % 4 == 0 here: ldc % 4 == 0 and the tail is masked on the way out)
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            if (p.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(stg + lane * 32 + (((q0 >> 2) ^ (lane & 7)) << 2)) = v;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3), g = lane & 7;
+            const float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((g ^ (row & 7)) << 2));
+            const int mr = m0 + lane_grp * 32 + row, n = n0 + cb + 4 * g;
+            if (mr < p.M && n + 3 < p.N) *reinterpret_cast<float4*>(p.c + (size_t)mr * p.ldc + n) = v;
+          }
+          __syncwarp();  // the block is read before the next one overwrites the buffer
+        } else if (m < p.M) {
 #pragma unroll
           for (int q0 = 0; q0 < 32; q0 += 4) {
             const int n = n0 + cb + q0;
@@ -455,7 +494,7 @@ tc_gemm_x3_persist_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
           }
         }
       }
-      if (p.path && m < p.M) {  // frame label as in decode.cu: -1 beyond the line, 0 = blank or below the threshold
+      if (p.path && chalf == 0 && m < p.M) {  // frame label as in decode.cu: -1 beyond the line, 0 = blank or below the threshold
         const int t = m / p.dec_B, b = m - t * p.dec_B;
         int label = -1;
         if (t < __ldg(p.lens + b)) label = (best_i == 0 || best_v < p.thresh) ? 0 : best_i;
@@ -922,7 +961,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
         cudaFuncSetAttribute(tc_gemm_x3_shortk_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kTcSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(tc_gemm_x3_persist_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kTcSmemBytes) != cudaSuccess)
+                             kTcPersistSmemBytes) != cudaSuccess)
       return VOCR_EXECUTION_FAILED;
     attr_latch.set();
   }
@@ -934,7 +973,7 @@ static int tc_gemm_launch(int a_mn, int b_mn, int M, int N, int K, const void* a
   }
   cudaError_t err = cudaSuccess;
   if (kind == 0) {  // persistent, one CTA per SM
-    tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcThreads, kTcSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p,
+    tc_gemm_x3_persist_kernel<F16><<<min(tiles, kNumSMs), kTcPersistThreads, kTcPersistSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p,
                                                                                              tiles_n, tiles);
   } else if (cm * cn == 1) {
     dim3 grid(tiles_n, tiles_m, splits);
