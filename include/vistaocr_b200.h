@@ -146,7 +146,8 @@ int vocr_conv3x3_c16_wgrad_f32(const float* x, const float* dz, float* dw, float
  *   permute+contiguous of cnnlstm.py:276).  a_hi / a_lo (both or neither; same layout as a) optionally receive the
  *   TF32 split planes the tensor-core conv of the next block reads (saves a vocr_split_tf32_f32 pass); dz_hi / dz_lo
  *   of vocr_bn_relu_bwd_f32 likewise.
- * vocr_bn_relu_bwd_f32: da (same strided layout) -> dz[B,H,W,C], dgamma, dbeta, dbias (= sum dz, the gradient of
+ * vocr_bn_relu_bwd_f32: da (same strided layout) -> dz[B,H,W,C] (may be NULL when only the FP16 pair planes dz_hi16 /
+ *   dz_lo16 are wanted: both gradient convolutions then read the planes), dgamma, dbeta, dbias (= sum dz, the gradient of
  *   the conv bias in front of the BatchNorm; may be NULL).  red_ws: float64[3*C] scratch.
  * FP16 pair planes (see vocr_split_f16_f32) come out of the same kernels without an extra pass over the tensor:
  *   vocr_bn_finalize_f32 aux (device float[2], optional): [0] = an upper bound of the activations - analytic with batch

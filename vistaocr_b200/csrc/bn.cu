@@ -220,7 +220,7 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__
       o.z = sc.z * (g2 - m1[2] - (v.z - mu.z) * is.z * m2[2]);
       o.w = sc.w * (g3 - m1[3] - (v.w - mu.w) * is.w * m2[3]);
       sb[0] += o.x; sb[1] += o.y; sb[2] += o.z; sb[3] += o.w;
-      *(reinterpret_cast<float4*>(dz) + p * C4 + c4) = o;
+      if (dz) *(reinterpret_cast<float4*>(dz) + p * C4 + c4) = o;  // (null: the consumers read the FP16 pair planes only)
       if (dz_hi) {
         float4 h, l;
         h.x = tf32_rna(o.x); l.x = tf32_rna(o.x - h.x);
@@ -346,13 +346,13 @@ extern "C" int vocr_bn_relu_bwd_f32(const float* da, const float* z, const float
                                     vocr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long P = (long long)B * H * W;
-  VOCR_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && red_ws && dz && dgamma && dbeta);
+  VOCR_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && red_ws && (dz || dz_hi16) && dgamma && dbeta);
   if (cudaMemsetAsync(red_ws, 0, sizeof(double) * 3 * C, stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
   VOCR_REQUIRE(dz_hi16 ? (dz_lo16 && scale_max && pair_state) : !dz_lo16);
   if (dz_hi16 && cudaMemsetAsync(pair_state, 0, 2 * sizeof(int32_t), stream) != cudaSuccess) return VOCR_MEMOPS_FAILED;
   if (P > 0) {
     VOCR_REQUIRE(da && z && scale && shift && save_mean && save_invstd);
-    VOCR_REQUIRE(aligned16(z) && aligned16(da) && aligned16(dz) && sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
+    VOCR_REQUIRE(aligned16(z) && aligned16(da) && (!dz || aligned16(dz)) && sB % 4 == 0 && sH % 4 == 0 && sW % 4 == 0);
     const int C4 = C / 4;
     const int rows = 256 / C4;
     long long rows_per_cta = ceil_div64(P, (long long)kNumSMs * 4);

@@ -547,7 +547,7 @@ class _ConvBNReLU(torch.autograd.Function):
         B, H, W, Cin, Cout, strides, training = ctx.dims
         dev = x.device
         da = _c(da)
-        dz = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
+        dz = torch.empty((B, H, W, Cout), dtype=F32, device=dev)  # (virtual until written: see planes_only below)
         dgamma = torch.empty((Cout,), dtype=F32, device=dev)
         dbeta = torch.empty((Cout,), dtype=F32, device=dev)
         dbias = torch.empty((Cout,), dtype=F32, device=dev)
@@ -559,9 +559,12 @@ class _ConvBNReLU(torch.autograd.Function):
         dz_hi16 = torch.empty(dz.shape, dtype=torch.float16, device=dev) if want16 else None
         dz_lo16 = torch.empty(dz.shape, dtype=torch.float16, device=dev) if want16 else None
         pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
+        # both gradient convolutions read the FP16 pair planes when their shapes allow it: the fp32 dz is then never read
+        # and not written (a third of this pass's stores)
+        planes_only = want16 and (Cin % 64 == 0 or _narrow(Cin, Cout)) and (Cin % 4 == 0 or not ctx.needs_input_grad[0])
         st = lib().vocr_bn_relu_bwd_f32(ptr(da), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
-                                        int(training), B, H, W, Cout, strides[0], strides[1], strides[2], ptr(dz),
-                                        ptr(dz_hi), ptr(dz_lo), ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red),
+                                        int(training), B, H, W, Cout, strides[0], strides[1], strides[2],
+                                        None if planes_only else ptr(dz), ptr(dz_hi), ptr(dz_lo), ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(red),
                                         ptr(dz_hi16), ptr(dz_lo16), _off(aux, 1) if want16 else None, ptr(pstate),
                                         stream())
         check(st, "vocr_bn_relu_bwd_f32")
