@@ -523,8 +523,8 @@ class _ConvBNReLU(torch.autograd.Function):
         pstate = torch.empty((2,), dtype=torch.int32, device=dev) if want16 else None
         # inference with a tensor-core conv as the only consumer (`planes`): that conv reads the planes, nobody reads the
         # fp32 activation - do not write it (the returned tensor then only carries the shape and the operand planes)
-        planes_only = allow_planes_only and want16 and not training and not torch.is_grad_enabled() and \
-            not x.requires_grad
+        # (training too: the consumer's backward multiplies by the planes as well - conv3x3_wgrad's FP16 path)
+        planes_only = allow_planes_only and want16
         st = lib().vocr_bn_relu_apply_f32(ptr(z), ptr(scale), ptr(shift), None if planes_only else ptr(a), ptr(a_hi),
                                           ptr(a_lo), B, H, W, Cout,
                                           strides[0], strides[1], strides[2], ptr(a_hi16), ptr(a_lo16),
@@ -584,8 +584,9 @@ def conv_bn_relu(x, weight, bias, gamma, beta, running_mean, running_var, traini
                  seq_layout=False, planes=True, allow_planes_only=False):
     """planes: the consumer is another tensor-core conv, so the apply kernel also emits the operand planes (pass False
     when a pooling layer follows - the planes would go unread).  allow_planes_only: the caller guarantees that a
-    tensor-core conv of this module is the ONLY consumer; in inference (eval statistics, no autograd) the fp32 activation
-    is then not written at all - the returned tensor carries the shape and the planes, its values are undefined."""
+    tensor-core conv of this module (Cin % 64 == 0: forward, weight gradient and data gradient all read the FP16 pair
+    planes) is the ONLY consumer; the fp32 activation is then not written at all - the returned tensor carries the shape
+    and the planes, its values are undefined."""
     Cin, Cout = x.shape[3], weight.shape[0]
     no_grad = not torch.is_grad_enabled() or not any(
         t is not None and t.requires_grad for t in (x, weight, bias, gamma, beta))
