@@ -252,7 +252,9 @@ conv_weight_layout_kernel(const float* __restrict__ w, int Cin, int Cout, float*
 // One thread = one pooled pixel x 4 output channels.  wk: [9*Cin][16].  arg (uint8, optional): which of the 4 window
 // positions won (first max in (dy,dx) scan order, like ATen max_pool2d), for the backward pass.
 constexpr int kRdsCout = 16;
-__global__ void __launch_bounds__(256)
+template <bool VEC4>  // VEC4: Cin % 4 == 0 and a 16-byte aligned x (second stage); separate instantiations keep the
+                      // one-channel first stage at its low register count
+__global__ void __launch_bounds__(256, VEC4 ? 2 : 3)
 rds_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
                float* __restrict__ y, uint8_t* __restrict__ arg, int B, int H, int W, int Cin) {
   extern __shared__ float s_w[];  // [9*Cin][16]
@@ -274,7 +276,7 @@ rds_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wk, const 
     for (int c = 0; c < 4; ++c) acc[p][c] = bias[cq * 4 + c];
   const int y0 = yo * 2 - 1, x0 = xo * 2 - 1;  // top-left of the 4x4 input patch
   const float* xb = x + (size_t)b * H * W * Cin;
-  if ((Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+  if (VEC4) {
     // channels four at a time: 16 float4 loads of the patch feed 576 multiply-adds (second stage, Cin = 16)
     for (int c4 = 0; c4 < Cin; c4 += 4) {
       float4 patch[4][4];
@@ -720,7 +722,10 @@ extern "C" int vocr_rds_fwd_f32(const float* x, const float* wk, const float* bi
   if (total == 0) return VOCR_OK;
   VOCR_REQUIRE(x && wk && bias && y && aligned16(y));
   const size_t smem = sizeof(float) * 9 * Cin * kRdsCout;
-  rds_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, smem, stream>>>(x, wk, bias, y, arg, B, H, W, Cin);
+  if ((Cin & 3) == 0 && aligned16(x))
+    rds_fwd_kernel<true><<<(unsigned)ceil_div64(total, 256), 256, smem, stream>>>(x, wk, bias, y, arg, B, H, W, Cin);
+  else
+    rds_fwd_kernel<false><<<(unsigned)ceil_div64(total, 256), 256, smem, stream>>>(x, wk, bias, y, arg, B, H, W, Cin);
   VOCR_CHECK_LAUNCH();
   return VOCR_OK;
 }
