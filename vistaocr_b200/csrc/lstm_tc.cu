@@ -538,22 +538,6 @@ struct LstmCbArgs {
   int T, B, H, US, NSL, MT, UT, Tmax, NG, n_items;  // UT = out units per M tile (a multiple of US), MT tiles
 };
 
-__device__ __forceinline__ bool cb_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void cb_wait_cluster_or_trap(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spins = 0; spins < (1u << 24); ++spins)
-    if (cb_try_wait_cluster(bar, parity)) return;
-  asm volatile("trap;");
-}
 // arrive on the mbarrier at the same offset as `bar` in CTA `rank` of the cluster
 __device__ __forceinline__ void cb_remote_arrive(uint64_t* bar, uint32_t rank) {
   asm volatile(
@@ -835,24 +819,16 @@ __global__ void __launch_bounds__(kCbThreads, 1) bilstm_bwd_cluster_kernel(LstmC
           __syncwarp();
           if (lane < NSL) cb_remote_arrive(&free_bar[slice], (uint32_t)lane);
         }
-        const float mxs[4] = {mx[0], mx[1], mx[2], mx[3]};
-        size_t tbs[4];
-        bool acts[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tbs[j] = tbq[j];
-          acts[j] = act[j];
-        }
-        if (k > 0) issue_loads(k - 1);
+        if (k > 0) issue_loads(k - 1);  // (writes raw / actn / tbn only: act / tbq still describe step k)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (acts[j]) {
-            float* dg = a.dgates + (tbs[j] * 2 + dir) * 4 * H + u0 + U;
+          if (act[j]) {
+            float* dg = a.dgates + (tbq[j] * 2 + dir) * 4 * H + u0 + U;
             dg[0] = da[j][0];
             dg[(size_t)H] = da[j][1];
             dg[(size_t)2 * H] = da[j][2];
             dg[(size_t)3 * H] = da[j][3];
-            da_max = fmaxf(da_max, mxs[j]);
+            da_max = fmaxf(da_max, mx[j]);
           }
         if (k == 0) break;
         CB_T(c4);
