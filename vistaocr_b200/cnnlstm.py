@@ -12,7 +12,6 @@ calls them - every stage runs through vistaocr_b200.ops.  Differences, all delib
   * LM decoding (`init_lm`, `decode_with_lm*`, needs the external EESEN decoder) is out of scope and raises.
 """
 import logging
-import math
 
 import torch
 import torch.nn as nn
